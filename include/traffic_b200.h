@@ -1,0 +1,172 @@
+/*
+ * traffic_b200.h - C ABI of libtraffic_b200.so, the B200 (sm_100a) implementation of
+ * the traffic-env simulation step.
+ *
+ * The reference (samanklesaria/traffic-env) has no FFI of its own: its boundary is
+ * the Python class gym_traffic.envs.traffic_env.TrafficEnv (traffic_env.py:221-394)
+ * plus the Repeater/Remi wrappers that sit on the tick loop (traffic_test.py:27-64).
+ * Each entry point below names the reference interface it replaces.  A maintainer
+ * binds these with ctypes from inside TrafficEnv.
+ *
+ * Conventions
+ *  - plain C, no torch/CUDA types in signatures; `stream` is a cudaStream_t passed as
+ *    void* (NULL = the handle's own stream);
+ *  - every function returns 0 on success, <0 on error (te_last_error() has the text);
+ *    simulation overflow is DATA (done[e] = 1), never an error (traffic_env.py:109-113,
+ *    246-248);
+ *  - `memspace` says where caller buffers live: TE_HOST (pageable or pinned host memory;
+ *    the call is synchronous) or TE_DEVICE (device memory on the handle's device; the
+ *    call is asynchronous on `stream`);
+ *  - E = num_envs, I = m*n intersections, r = 4*I train roads, R = r + 2m + 2n roads
+ *    (roadgraph.py:30-33), CAP = 20 ring slots (traffic_env.py:24);
+ *  - one handle = one device = one contiguous block of env instances; a handle may be
+ *    used from one thread at a time, different handles from different threads freely
+ *    (a3c.py:69-72 steps envs from several Python threads).
+ */
+#ifndef TRAFFIC_B200_H
+#define TRAFFIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TE_CAP 20
+#define TE_PARAMS 10
+
+enum te_memspace { TE_HOST = 0, TE_DEVICE = 1 };
+
+enum te_flags {
+  TE_LEARN_SWITCH = 1 << 0, /* FLAGS.learn_switch, traffic_env.py:225-230 */
+  TE_REMI = 1 << 1,         /* te_step returns remi_reward() (traffic_test.py:59-64) instead of the summed env reward */
+  TE_AUTO_RESET = 1 << 2,   /* an env that finished (overflow or episode_len) is _reset at the start of its next te_step */
+  TE_VALIDATE = 1 << 3      /* FLAGS.mode == 'validate': record trip times (traffic_env.py:139-157) */
+};
+
+enum te_arrival_mode {
+  TE_ARRIVALS_NONE = 0,
+  TE_ARRIVALS_INJECTED = 1, /* replay a schedule given with te_set_arrivals (equivalence runs) */
+  TE_ARRIVALS_PHILOX = 2    /* counter-based Philox4x32-10 stream, same process as poisson() (traffic_env.py:160-164) */
+};
+
+typedef struct te_config {
+  int32_t struct_size;   /* = sizeof(te_config) */
+  int32_t m, n;          /* GridRoad(m, n, length), roadgraph.py:26 */
+  float length;          /* road length in metres */
+  float rate;            /* FLAGS.rate: seconds per tick, traffic_env.py:12 */
+  int32_t num_envs;      /* env instances on this device */
+  int64_t env_id_base;   /* global id of local env 0 (keys the Philox stream; makes results independent of sharding) */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t flags;         /* te_flags */
+  uint32_t entry_spec;   /* generate_entrypoints(spec), roadgraph.py:42-51: bit k set = side k closed */
+  int32_t arrival_mode;  /* te_arrival_mode */
+  double cars_per_tick;  /* FLAGS.cars_per_sec * FLAGS.rate (traffic_env.py:161, 394); Philox mode */
+  uint64_t seed;         /* Philox key (with the global env id) */
+  int32_t episode_len;   /* actor steps per episode for TE_AUTO_RESET (0 = only overflow ends an episode) */
+  float gamma;           /* FLAGS.gamma for the discounted return statistic (util.py:68-94) */
+  float archetype[TE_PARAMS]; /* x,v,l,a,delta,v0,b,T,s0,w of a new car, traffic_env.py:33-43 */
+} te_config;
+
+typedef struct te_dims {
+  int32_t m, n, intersections, train_roads, roads, roads_padded, num_envs, num_entry;
+  int32_t obs_raw;   /* 2r + 2I ints: TrafficEnv.obs, traffic_env.py:370-376 */
+  int32_t obs_actor; /* 2r + I floats: Repeater observation, traffic_test.py:33 */
+} te_dims;
+
+typedef struct te_stats {
+  uint64_t ticks;            /* env-ticks executed */
+  uint64_t actor_steps;      /* env actor steps executed by te_step */
+  uint64_t vehicle_updates;  /* real cars advanced by one tick (one element of one sim() call) */
+  uint64_t overflows;        /* cars dropped on a full ring */
+  uint64_t cars_generated;
+  uint64_t episodes;         /* episodes closed by TE_AUTO_RESET / te_reset */
+  double return_sum;         /* sum over closed episodes of sum_t mean_i reward (util.py:75) */
+  double disc_return_sum;    /* same with gamma^t weighting */
+  uint64_t seq_fallback_ticks; /* env-ticks whose transfer phase ran in strict road order */
+} te_stats;
+
+typedef struct te_handle te_handle;
+
+/* Fills cfg with the reference defaults (traffic_env.py:11-25,33-43; traffic_test.py:80): 3x3 grid,
+   length 250, rate 0.5, one env, Philox arrivals at 0.12 cars/s per side-lane. */
+void te_default_config(te_config *cfg);
+
+/* TrafficEnv.set_graph + seed_generator + reset_entrypoints (traffic_env.py:361-382, 250-253, 389-394)
+   for num_envs instances; uploads the topology tables of GridRoad (roadgraph.py:26-64). */
+int te_create(const te_config *cfg, te_handle **out);
+int te_destroy(te_handle *h);
+int te_get_dims(const te_handle *h, te_dims *out);
+const char *te_last_error(void);
+
+/* Topology tables as the device holds them (for tests): dest/nexts/phases int32[R], entry int32[num_entry]. */
+int te_get_topology(const te_handle *h, int32_t *dest, int32_t *nexts, int32_t *phases, int32_t *entry);
+
+/* TrafficEnv._reset (traffic_env.py:259-272) for the envs whose mask byte is non-zero (NULL = all).
+   init_phase uint8[E, I] replaces action_space.sample(); NULL draws from the Philox stream. */
+int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *init_phase, int memspace, void *stream);
+
+/* Injected arrival schedule (TE_ARRIVALS_INJECTED).  CSR over (env, tick): the entry roads of
+   env e at schedule tick t are roads[offsets[e*(horizon+1)+t] .. offsets[e*(horizon+1)+t+1]) in
+   arrival order; offsets are absolute into roads.  Replaces the rand_car/rand pair that
+   add_new_cars pulls from (traffic_env.py:274-283).  The schedule cursor of an env advances by
+   one per tick executed and is NOT rewound by reset (the reference never re-seeds).
+   Ticks past the horizon have no arrivals.  Buffers are copied; always host pointers. */
+int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int32_t horizon);
+
+/* One actor step = Repeater(k_ticks)._step (+ Remi when TE_REMI) for every env, one kernel launch
+   (traffic_test.py:37-64).  actions uint8[E, I] (non-zero = 1); obs float[E, 2r+I];
+   reward float[E, I]; done uint8[E].  The tick loop of an env stops after the tick that overflowed. */
+int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
+            int memspace, void *stream);
+
+/* One physics tick = bare TrafficEnv._step (traffic_env.py:224-248): obs int32[E, 2r+2I]
+   (passed | detected | current_phase | elapsed), reward float[E, I], done uint8[E]. */
+int te_step_raw(te_handle *h, const uint8_t *actions, int32_t *obs, float *reward, uint8_t *done, int memspace,
+                void *stream);
+
+/* TrafficEnv.remi_reward (traffic_env.py:384-387, 64-78): reward float[E, I]; clears waiting and passed_dst. */
+int te_remi_reward(te_handle *h, float *reward, int memspace, void *stream);
+
+/* cars_on_roads (traffic_env.py:214-218): out int32[E, R]. */
+int te_cars_on_roads(te_handle *h, int32_t *out, int memspace, void *stream);
+
+/* Device-resident greedy controller (algorithms/greedy.py:14-16): actions[e, i] =
+   (cars(E-bound) + cars(W-bound) - cars(S-bound) - cars(N-bound)) < 0 at intersection i. */
+int te_greedy_actions(te_handle *h, uint8_t *actions, int memspace, void *stream);
+
+/* Full state of envs [env_begin, env_begin+count) in the reference's layout, host pointers, any may be
+   NULL: leading/lastcar int32[count,R]; x, v float[count,R,20] (only live slots and the leading slot are
+   meaningful, as in the reference); obs int32[count,2r+2I]; waiting int32[count,r];
+   passed_dst uint8[count,I]; steps float[count]. */
+int te_get_state(te_handle *h, int32_t env_begin, int32_t count, int32_t *leading, int32_t *lastcar, float *x,
+                 float *v, int32_t *obs, int32_t *waiting, uint8_t *passed_dst, float *steps);
+int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *leading, const int32_t *lastcar,
+                 const float *x, const float *v, const int32_t *obs, const int32_t *waiting,
+                 const uint8_t *passed_dst, const float *steps);
+
+/* Counters since te_create (device -> host; synchronises the handle's stream). */
+int te_get_stats(te_handle *h, te_stats *out);
+
+/* Trip times recorded in validate mode (traffic_env.py:154), seconds; returns the number available
+   through *count and copies up to cap of them.  Clears the buffer when `clear` is non-zero. */
+int te_get_trip_times(te_handle *h, float *out, int64_t cap, int64_t *count, int clear);
+
+int te_synchronize(te_handle *h);
+
+/* Kernel time of the last te_step/te_step_raw launch in milliseconds (CUDA events on the launch stream). */
+int te_last_kernel_ms(te_handle *h, float *ms);
+
+/* ---- test hooks (host pointers): device arithmetic exposed for bit-exactness tests */
+/* out[i] = device restatement of glibc powf(x[i], y) (numba lowers float32 ** to libm powf). */
+int te_test_powf(int device, const float *x, float y, float *out, int64_t n);
+/* One IDM update per element (traffic_env.py:50-62): follower (x,v) behind leader (xl,vl,ll). */
+int te_test_idm(int device, float rate, const float *archetype, const float *xl, const float *vl, const float *ll,
+                const float *x, const float *v, float *x_out, float *v_out, int64_t n);
+/* Philox4x32-10 block: out[4] for counter ctr[4], key[2]. */
+int te_test_philox(int device, const uint32_t *ctr, const uint32_t *key, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAFFIC_B200_H */

@@ -63,6 +63,8 @@ def lib():
         L.to_powf_compare.restype = C.c_long
         L.to_powf_compare.argtypes = [pf, C.c_long, f32, C.POINTER(C.c_long)]
         L.to_sim_kernel.argtypes = [f32, f32, f32, f32, pf, pf, pf]
+        L.to_sim_bulk.argtypes = [f32, pf, pf, pf, pf, pf, pf, C.c_long, pf, pf]
+        L.to_powf_bulk.argtypes = [pf, f32, C.c_long, pf]
         L.to_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.to_philox_seed.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), i32]
         L.to_philox_arrivals.restype = i32
@@ -232,3 +234,27 @@ def philox4x32_10(ctr, key):
     o = (C.c_uint32 * 4)()
     L.to_philox4x32_10(c, k, o)
     return [int(v) for v in o]
+
+
+def _pf(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def sim_bulk(rate, xL, vL, lL, x, v, arch):
+    """Oracle IDM update (traffic_env.py:50-62) for arrays of (leader, follower) pairs."""
+    L = lib()
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (xL, vL, lL, x, v)]
+    a = np.ascontiguousarray(arch, dtype=np.float32)
+    n = arrs[0].size
+    xo, vo = np.empty(n, np.float32), np.empty(n, np.float32)
+    L.to_sim_bulk(float(rate), *[_pf(t) for t in arrs], _pf(a), n, _pf(xo), _pf(vo))
+    return xo, vo
+
+
+def powf_bulk(x, y):
+    """Host libm powf (what numba calls for float32 ** float32)."""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    L.to_powf_bulk(_pf(x), float(y), x.size, _pf(out))
+    return out

@@ -1,0 +1,114 @@
+"""GPU: device arithmetic against the host, bit for bit (through the C-ABI test hooks)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from traffic_env_b200 import _lib
+    return _lib.load(), _lib
+
+
+def gpu_powf(x, y):
+    L, m = _lib()
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    m.check(L.te_test_powf(0, x.ctypes.data, float(y), out.ctypes.data, x.size))
+    return out
+
+
+def gpu_idm(rate, arch, xl, vl, ll, x, v):
+    L, m = _lib()
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (xl, vl, ll, x, v)]
+    a = np.ascontiguousarray(arch, np.float32)
+    xo, vo = np.empty_like(arrs[0]), np.empty_like(arrs[0])
+    m.check(L.te_test_idm(0, float(rate), a.ctypes.data, *[t.ctypes.data for t in arrs], xo.ctypes.data,
+                          vo.ctypes.data, arrs[0].size))
+    return xo, vo
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))
+
+
+@pytest.mark.parametrize("y", [4.0, 2.5, 1.0, 0.37])
+def test_powf_matches_host_libm(y):
+    """numba lowers float32 ** float32 to libm powf; the device restates glibc's algorithm."""
+    rng = np.random.RandomState(5)
+    x = np.concatenate([
+        rng.uniform(0, 2, 3_000_000).astype(np.float32),
+        (np.abs(rng.standard_normal(500_000)) * 1e-3).astype(np.float32),
+        rng.randint(0, 0x7f800000, 2_000_000, dtype=np.int64).astype(np.uint32).view(np.float32),
+        np.arange(0, 0x00800000, 4099, dtype=np.uint32).view(np.float32),  # subnormals
+        np.array([0, 1e-45, 1e-40, 1.17549435e-38, 1, np.inf, np.nan, 3e38, 0.79985, 13.88 / 13.89], np.float32)])
+    got, want = gpu_powf(x, y), orc.powf_bulk(x, y)
+    bad = ~same_bits(got, want)
+    assert not bad.any(), "first mismatch x=%r got=%r want=%r" % (x[bad][0], got[bad][0], want[bad][0])
+
+
+def test_powf_all_velocity_ratios():
+    """Every float32 in [0, 1.25] that v / v0 can take on a coarse lattice plus its neighbours."""
+    base = np.arange(0, np.float32(1.25).view(np.uint32), 257, dtype=np.uint32)
+    x = np.concatenate([base, base + 1, base + 2]).view(np.float32)
+    got, want = gpu_powf(x, 4.0), orc.powf_bulk(x, 4.0)
+    assert same_bits(got, want).all()
+
+
+def test_idm_update_matches_oracle():
+    rng = np.random.RandomState(11)
+    n = 2_000_000
+    arch = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], np.float32)
+    x = rng.uniform(-50, 260, n).astype(np.float32)
+    gap = np.where(rng.rand(n) < 0.3, rng.uniform(0, 8, n), rng.uniform(0, 300, n))
+    xl = (x + gap + 4).astype(np.float32)
+    v = np.where(rng.rand(n) < 0.2, 0, rng.uniform(0, 15, n)).astype(np.float32)
+    vl = np.where(rng.rand(n) < 0.3, 0, rng.uniform(0, 15, n)).astype(np.float32)
+    ll = np.where(rng.rand(n) < 0.2, 0, 4).astype(np.float32)
+    # virtual leaders: red light at the road end and free road (+inf), plus collisions (negative gap)
+    xl[:50000] = 250.0
+    xl[50000:100000] = np.inf
+    vl[:100000] = 0
+    ll[:100000] = 0
+    xl[100000:110000] = x[100000:110000] - 1.0
+    v[110000:111000] = 1e-30
+    v[111000:112000] = 1e-42
+    gx, gv = gpu_idm(0.5, arch, xl, vl, ll, x, v)
+    ox, ov = orc.sim_bulk(0.5, xl, vl, ll, x, v, arch)
+    bx, bv = ~same_bits(gx, ox), ~same_bits(gv, ov)
+    assert not bx.any() and not bv.any(), "x mismatches %d, v mismatches %d" % (bx.sum(), bv.sum())
+
+
+def test_idm_other_rate_and_archetype():
+    rng = np.random.RandomState(12)
+    n = 300_000
+    arch = np.array([0.0, 8.0, 5.5, 1.7, 3.0, 20.0, 2.3, 1.4, 2.0, 0.0], np.float32)
+    x = rng.uniform(0, 500, n).astype(np.float32)
+    xl = (x + rng.uniform(0, 100, n)).astype(np.float32)
+    v = rng.uniform(0, 25, n).astype(np.float32)
+    vl = rng.uniform(0, 25, n).astype(np.float32)
+    ll = np.full(n, 5.5, np.float32)
+    gx, gv = gpu_idm(0.25, arch, xl, vl, ll, x, v)
+    ox, ov = orc.sim_bulk(0.25, xl, vl, ll, x, v, arch)
+    assert same_bits(gx, ox).all() and same_bits(gv, ov).all()
+
+
+def test_philox_block_matches_oracle():
+    L, m = _lib()
+    rng = np.random.RandomState(3)
+    for _ in range(64):
+        ctr = rng.randint(0, 2**32, 4, dtype=np.int64).astype(np.uint32)
+        key = rng.randint(0, 2**32, 2, dtype=np.int64).astype(np.uint32)
+        out = np.empty(4, np.uint32)
+        m.check(L.te_test_philox(0, ctr.ctypes.data, key.ctypes.data, out.ctypes.data))
+        assert list(out) == orc.philox4x32_10(ctr, key)
+    # known-answer vector of the Random123 distribution (philox4x32-10, all-zero counter and key)
+    z = np.zeros(4, np.uint32)
+    out = np.empty(4, np.uint32)
+    m.check(L.te_test_philox(0, z.ctypes.data, z[:2].ctypes.data, out.ctypes.data))
+    assert [hex(int(v)) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]

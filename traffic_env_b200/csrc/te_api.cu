@@ -1,0 +1,596 @@
+// te_api.cu - host side of libtraffic_b200.so (C ABI declared in include/traffic_b200.h).
+//
+// Builds the GridRoad topology tables (reference: gym_traffic/envs/roadgraph.py:26-64),
+// owns the device state of num_envs env instances, and launches the kernels in
+// te_kernels.cuh.  There is no CPU implementation of the simulation in this library:
+// every entry point either runs on the CUDA device or fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/traffic_b200.h"
+#include "te_kernels.cuh"
+
+using namespace te;
+
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+static int fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct te_handle {
+  te_config cfg;
+  int V, r, R, Rp, I, n_entry, G;
+  int device;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  bool timed;
+  StepParams base;  // everything except per-call pointers
+  std::vector<int> dest, nexts, phases, entry;
+  // device buffers
+  float *x, *v;
+  int *elapsed;
+  uint8_t *phase, *passed_dst;
+  EnvScalars *env;
+  DeviceStats *stats;
+  short *d_nexts, *d_up, *d_entry_roads;
+  signed char *d_entry_idx;
+  long long *d_sched_off;
+  short *d_sched_roads;
+  uint32_t *d_gap_cdf;
+  // staging for TE_HOST calls
+  uint8_t *d_actions, *d_done, *d_mask, *d_init_phase;
+  float *d_obs_f, *d_reward;
+  int *d_obs_i, *d_cars;
+  float *d_trips; unsigned long long *d_trip_count; long long trip_cap;
+  int warps;
+  int smem_optin;
+};
+
+extern "C" const char *te_last_error(void) { return g_err.c_str(); }
+
+extern "C" void te_default_config(te_config *c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(te_config);
+  c->m = 3; c->n = 3; c->length = 250.f; c->rate = 0.5f;   // traffic_test.py:80, traffic_env.py:12
+  c->num_envs = 1; c->env_id_base = 0; c->device = 0;
+  c->flags = TE_REMI;                                     // traffic_test.py:17 (--remi True)
+  c->entry_spec = 0;                                      // FLAGS.entry == 'all', traffic_env.py:392
+  c->arrival_mode = TE_ARRIVALS_PHILOX;
+  c->cars_per_tick = 0.12 * 3 * 4 * 0.5;                  // local_cars_per_sec * m * inv_popcount(0) * rate
+  c->seed = 0; c->episode_len = 0; c->gamma = 0.8f;       // alg_flags.py:13
+  const float arch[TE_PARAMS] = {0.f, 11.11f, 4.f, 3.f, 4.f, 13.89f, 6.f, 2.f, 1.f, 0.f};  // traffic_env.py:35-43
+  memcpy(c->archetype, arch, sizeof(arch));
+}
+
+// roadgraph.py:54-64
+static int grid_next(int i, int m, int n) {
+  const int v = m * n;
+  if (i >= 4 * v) return -1;
+  const int col = i % n, row = (i % v) / n;
+  if (i < v) return col < n - 1 ? i + 1 : 4 * v + n + row;
+  if (i < 2 * v) return col > 0 ? i - 1 : 4 * v + 2 * n + m + row;
+  if (i < 3 * v) return row < m - 1 ? i + n : 4 * v + n + m + col;
+  return row > 0 ? i - n : 4 * v + col;
+}
+
+// Thresholds T[k] = floor(2^32 * P(round(Exp(scale)) <= k)), scale = 1 / cars_per_tick ticks.
+// round() is Python's round-half-even; ties have measure zero, so P(gap <= k) = 1 - exp(-(k + 0.5) / scale).
+// Built on the host in double and shared verbatim with the CPU oracle (traffic_env_b200/arrivals.py builds
+// the same table for tests), so no transcendental is evaluated on the device.
+static std::vector<uint32_t> build_gap_cdf(double cars_per_tick) {
+  std::vector<uint32_t> t;
+  if (!(cars_per_tick > 0)) return t;
+  for (int k = 0; k < 8192; k++) {
+    const double cdf = -expm1(-(k + 0.5) * cars_per_tick);
+    const double scaled = floor(cdf * 4294967296.0);
+    if (scaled >= 4294967295.0) break;
+    t.push_back((uint32_t)scaled);
+  }
+  return t;
+}
+
+static void free_handle(te_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  void *ptrs[] = {h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
+                  h->d_entry_roads, h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
+                  h->d_done, h->d_mask, h->d_init_phase, h->d_reward, h->d_obs_i /* d_obs_f aliases it */, h->d_cars,
+                  h->d_trips, h->d_trip_count};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int te_destroy(te_handle *h) { free_handle(h); return 0; }
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
+
+extern "C" int te_create(const te_config *cfg, te_handle **out) {
+  if (!cfg || !out) return fail("te_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(te_config)) return fail("te_create: te_config size mismatch (%d vs %zu)", cfg->struct_size, sizeof(te_config));
+  if (cfg->m < 1 || cfg->n < 1 || cfg->num_envs < 1) return fail("te_create: bad dimensions");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("te_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("te_create: device %d out of range", cfg->device);
+  te_handle *h = new te_handle();
+  memset((void *)&h->base, 0, sizeof(h->base));
+  h->cfg = *cfg; h->device = cfg->device;
+  h->x = h->v = nullptr; h->elapsed = nullptr; h->phase = h->passed_dst = nullptr; h->env = nullptr; h->stats = nullptr;
+  h->d_nexts = h->d_up = h->d_entry_roads = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
+  h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
+  h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
+  h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->timed = false; h->trip_cap = 0;
+#define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CUH(cudaSetDevice(h->device));
+  const int m = cfg->m, n = cfg->n;
+  h->V = m * n; h->I = h->V; h->r = 4 * h->V; h->R = h->r + 2 * n + 2 * m;
+  h->Rp = (h->R + GROUP_ROADS - 1) / GROUP_ROADS * GROUP_ROADS;
+  h->G = h->Rp / GROUP_ROADS;
+  if (h->Rp > 32000) { free_handle(h); return fail("te_create: grid too large"); }
+  // topology (roadgraph.py:35-39, 42-51)
+  h->dest.resize(h->R); h->nexts.resize(h->R); h->phases.resize(h->R);
+  std::vector<short> nx(h->Rp, -1), up(h->Rp, -1);
+  std::vector<signed char> eidx(h->Rp, -1);
+  for (int i = 0; i < h->R; i++) {
+    h->phases[i] = (i / h->V) < 2;
+    h->dest[i] = i < 4 * h->V ? i % h->V : -1;
+    h->nexts[i] = grid_next(i, m, n);
+    nx[i] = (short)h->nexts[i];
+  }
+  for (int i = 0; i < h->R; i++) if (h->nexts[i] >= 0) {
+    if (up[h->nexts[i]] != -1) { free_handle(h); return fail("te_create: successor table is not injective"); }
+    up[h->nexts[i]] = (short)i;
+  }
+  const uint32_t spec = cfg->entry_spec;
+  const int v = h->V;
+  if ((spec & 1) == 0) for (int i = 0; i < m; i++) h->entry.push_back(n * i);
+  if (((spec >> 1) & 1) == 0) for (int i = 1; i <= m; i++) h->entry.push_back(v + n * i - 1);
+  if (((spec >> 2) & 1) == 0) for (int i = 0; i < n; i++) h->entry.push_back(2 * v + i);
+  if (((spec >> 3) & 1) == 0) for (int i = 0; i < n; i++) h->entry.push_back(3 * v + n * (m - 1) + i);
+  h->n_entry = (int)h->entry.size();
+  if (h->n_entry > 127) { free_handle(h); return fail("te_create: more than 127 entry roads"); }
+  std::vector<short> eroads(h->n_entry > 0 ? h->n_entry : 1, 0);
+  for (int k = 0; k < h->n_entry; k++) { eroads[k] = (short)h->entry[k]; eidx[h->entry[k]] = (signed char)k; }
+
+  const size_t E = (size_t)cfg->num_envs;
+  CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
+  CUH(dalloc(&h->x, E * h->Rp * CAP)); CUH(dalloc(&h->v, E * h->Rp * CAP));
+  CUH(dalloc(&h->elapsed, E * h->I)); CUH(dalloc(&h->phase, E * h->I)); CUH(dalloc(&h->passed_dst, E * h->I));
+  CUH(dalloc(&h->env, E)); CUH(dalloc(&h->stats, 1));
+  CUH(dalloc(&h->d_nexts, (size_t)h->Rp)); CUH(dalloc(&h->d_up, (size_t)h->Rp));
+  CUH(dalloc(&h->d_entry_idx, (size_t)h->Rp)); CUH(dalloc(&h->d_entry_roads, eroads.size()));
+  CUH(dalloc(&h->d_actions, E * h->I)); CUH(dalloc(&h->d_done, E)); CUH(dalloc(&h->d_mask, E));
+  CUH(dalloc(&h->d_init_phase, E * h->I));
+  CUH(dalloc(&h->d_obs_i, E * (2 * h->r + 2 * h->I)));
+  CUH(dalloc(&h->d_reward, E * h->I));
+  h->d_obs_f = reinterpret_cast<float *>(h->d_obs_i);  // raw and fused observations are never live together
+  CUH(cudaMemcpy(h->d_nexts, nx.data(), nx.size() * sizeof(short), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_up, up.data(), up.size() * sizeof(short), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_entry_idx, eidx.data(), eidx.size(), cudaMemcpyHostToDevice));
+  CUH(cudaMemcpy(h->d_entry_roads, eroads.data(), eroads.size() * sizeof(short), cudaMemcpyHostToDevice));
+  CUH(cudaMemset(h->stats, 0, sizeof(DeviceStats)));
+  CUH(cudaMemset(h->x, 0, E * h->Rp * CAP * sizeof(float)));
+  CUH(cudaMemset(h->v, 0, E * h->Rp * CAP * sizeof(float)));
+  CUH(cudaMemset(h->elapsed, 0, E * h->I * sizeof(int)));
+  CUH(cudaMemset(h->phase, 0, E * h->I)); CUH(cudaMemset(h->passed_dst, 0, E * h->I));
+  CUH(cudaMemset(h->d_done, 0, E));
+
+  std::vector<uint32_t> cdf = build_gap_cdf(cfg->cars_per_tick);
+  if (cfg->arrival_mode == TE_ARRIVALS_PHILOX && (cdf.empty() || h->n_entry == 0)) {
+    free_handle(h); return fail("te_create: Philox arrivals need cars_per_tick > 0 and at least one entry road");
+  }
+  CUH(dalloc(&h->d_gap_cdf, cdf.size()));
+  if (!cdf.empty()) CUH(cudaMemcpy(h->d_gap_cdf, cdf.data(), cdf.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+  // per-env scalars; the Philox stream draws its first gap at seeding time, like poisson() does on first next()
+  std::vector<EnvScalars> es(E);
+  for (size_t i = 0; i < E; i++) {
+    memset(&es[i], 0, sizeof(EnvScalars));
+    es[i].ep_mult = 1.0;
+  }
+  CUH(cudaMemcpy(h->env, es.data(), E * sizeof(EnvScalars), cudaMemcpyHostToDevice));
+
+  StepParams &p = h->base;
+  p.V = h->V; p.r = h->r; p.R = h->R; p.Rp = h->Rp; p.I = h->I; p.n_entry = h->n_entry; p.G = h->G;
+  p.num_envs = cfg->num_envs; p.length = cfg->length; p.det_thr = (double)cfg->length - 10.0;
+  p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
+  p.gamma = cfg->gamma;
+  const float *a = cfg->archetype;
+  p.idm.rate = cfg->rate; p.idm.x_new = a[0]; p.idm.v_new = a[1]; p.idm.len = a[2]; p.idm.a = a[3];
+  p.idm.delta = a[4]; p.idm.v0 = a[5]; p.idm.T = a[7]; p.idm.s0 = a[8];
+  { volatile float ab = a[3] * a[6]; p.idm.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
+  p.idm.len_plus = 0.f;
+  p.x = h->x; p.v = h->v; p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
+  p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
+  p.entry_roads = h->d_entry_roads; p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
+  p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
+  p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0;
+
+  // warps per CTA: enough to cover the road groups in few balanced rounds
+  int warps = h->G <= 16 ? h->G : 0;
+  if (!warps) {
+    int best = 16, best_waste = 1 << 30;
+    for (int w = 16; w >= 8; w--) {
+      const int rounds = (h->G + w - 1) / w, waste = rounds * w - h->G;
+      if (waste < best_waste) { best_waste = waste; best = w; }
+    }
+    warps = best;
+  }
+  if (warps < 2) warps = 2;
+  if (const char *ev = getenv("TE_WARPS")) { const int w = atoi(ev); if (w >= 1 && w <= MAX_THREADS / 32) warps = w; }
+  h->warps = warps;
+  CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry);
+  if (L.total > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", L.total, h->smem_optin); }
+  CUH(cudaFuncSetAttribute(te_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+
+  // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
+  te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
+  CUH(cudaGetLastError());
+  CUH(cudaMemsetAsync(h->phase, 0, E * h->I, h->stream));
+  // seed the arrival stream (draw 0 is the initial gap)
+  if (cfg->arrival_mode == TE_ARRIVALS_PHILOX) {
+    // done on the host: one Philox block per env, identical integer arithmetic
+    for (size_t i = 0; i < E; i++) {
+      uint32_t c[4] = {0, 0, 0, 0}, k[2] = {p.seed, (uint32_t)(cfg->env_id_base + (int64_t)i)};
+      for (int rd = 0; rd < 10; rd++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+      }
+      size_t lo = 0, hi = cdf.size();
+      while (lo < hi) { const size_t mid = (lo + hi) / 2; if (cdf[mid] <= c[0]) lo = mid + 1; else hi = mid; }
+      es[i].ph_skip = (uint32_t)lo; es[i].ph_draw = 1; es[i].reset_count = 1;
+    }
+    CUH(cudaStreamSynchronize(h->stream));
+    CUH(cudaMemcpy(h->env, es.data(), E * sizeof(EnvScalars), cudaMemcpyHostToDevice));
+  }
+  CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+  *out = h;
+  return 0;
+}
+
+extern "C" int te_get_dims(const te_handle *h, te_dims *d) {
+  if (!h || !d) return fail("te_get_dims: null argument");
+  d->m = h->cfg.m; d->n = h->cfg.n; d->intersections = h->I; d->train_roads = h->r; d->roads = h->R;
+  d->roads_padded = h->Rp; d->num_envs = h->cfg.num_envs; d->num_entry = h->n_entry;
+  d->obs_raw = 2 * h->r + 2 * h->I; d->obs_actor = 2 * h->r + h->I;
+  return 0;
+}
+
+extern "C" int te_get_topology(const te_handle *h, int32_t *dest, int32_t *nexts, int32_t *phases, int32_t *entry) {
+  if (!h) return fail("te_get_topology: null handle");
+  if (dest) memcpy(dest, h->dest.data(), h->R * sizeof(int));
+  if (nexts) memcpy(nexts, h->nexts.data(), h->R * sizeof(int));
+  if (phases) memcpy(phases, h->phases.data(), h->R * sizeof(int));
+  if (entry) memcpy(entry, h->entry.data(), h->n_entry * sizeof(int));
+  return 0;
+}
+
+static cudaStream_t pick_stream(te_handle *h, void *stream) { return stream ? (cudaStream_t)stream : h->stream; }
+
+extern "C" int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *init_phase, int memspace, void *stream) {
+  if (!h) return fail("te_reset: null handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = pick_stream(h, stream);
+  const size_t E = (size_t)h->cfg.num_envs;
+  const uint8_t *dm = env_mask, *dp = init_phase;
+  if (memspace == TE_HOST) {
+    if (env_mask) { CU(cudaMemcpyAsync(h->d_mask, env_mask, E, cudaMemcpyHostToDevice, st)); dm = h->d_mask; }
+    if (init_phase) { CU(cudaMemcpyAsync(h->d_init_phase, init_phase, E * h->I, cudaMemcpyHostToDevice, st)); dp = h->d_init_phase; }
+  }
+  te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(h->base, dm, dp, 0);
+  CU(cudaGetLastError());
+  if (memspace == TE_HOST) CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int32_t horizon) {
+  if (!h || !offsets || horizon < 0) return fail("te_set_arrivals: bad argument");
+  CU(cudaSetDevice(h->device));
+  const size_t E = (size_t)h->cfg.num_envs, no = E * ((size_t)horizon + 1);
+  const int64_t total = offsets[no - 1];
+  for (size_t e = 0; e < E; e++)
+    for (int t = 0; t < horizon; t++)
+      if (offsets[e * (horizon + 1) + t] > offsets[e * (horizon + 1) + t + 1]) return fail("te_set_arrivals: offsets not monotone");
+  std::vector<signed char> is_entry(h->R, 0);
+  for (int rd : h->entry) is_entry[rd] = 1;
+  for (int64_t k = 0; k < total; k++)
+    if (roads[k] < 0 || roads[k] >= h->R || !is_entry[roads[k]]) return fail("te_set_arrivals: road %d is not an entry road", (int)roads[k]);
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->d_sched_off) { cudaFree(h->d_sched_off); h->d_sched_off = nullptr; }
+  if (h->d_sched_roads) { cudaFree(h->d_sched_roads); h->d_sched_roads = nullptr; }
+  CU(dalloc(&h->d_sched_off, no)); CU(dalloc(&h->d_sched_roads, (size_t)(total > 0 ? total : 1)));
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  CU(cudaMemcpy(h->d_sched_off, offsets, no * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (total > 0) CU(cudaMemcpy(h->d_sched_roads, roads, (size_t)total * sizeof(int16_t), cudaMemcpyHostToDevice));
+  h->base.sched_off = h->d_sched_off; h->base.sched_roads = h->d_sched_roads; h->base.horizon = horizon;
+  return 0;
+}
+
+static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, void *obs, float *reward, uint8_t *done,
+                       int memspace, void *stream) {
+  if (!h || !actions || !obs || !reward || !done) return fail("te_step: null argument");
+  if (K < 1 || K > MAX_K) return fail("te_step: k_ticks must be in [1, %d]", MAX_K);
+  if (h->cfg.arrival_mode == TE_ARRIVALS_INJECTED && !h->base.sched_off) return fail("te_step: no arrival schedule set");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = pick_stream(h, stream);
+  const size_t E = (size_t)h->cfg.num_envs;
+  const size_t obs_len = raw ? (size_t)(2 * h->r + 2 * h->I) : (size_t)(2 * h->r + h->I);
+  StepParams p = h->base;
+  p.K = K; p.raw = raw;
+  if (memspace == TE_HOST) {
+    CU(cudaMemcpyAsync(h->d_actions, actions, E * h->I, cudaMemcpyHostToDevice, st));
+    p.actions = h->d_actions; p.obs_f = h->d_obs_f; p.obs_i = h->d_obs_i; p.reward = h->d_reward; p.done = h->d_done;
+  } else {
+    p.actions = actions; p.obs_f = (float *)obs; p.obs_i = (int *)obs; p.reward = reward; p.done = done;
+  }
+  if (!raw && (h->cfg.flags & TE_AUTO_RESET)) {
+    te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, nullptr, nullptr, 1);
+    CU(cudaGetLastError());
+  }
+  const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry);
+  CU(cudaEventRecord(h->ev0, st));
+  te_step_kernel<<<h->cfg.num_envs, h->warps * 32, L.total, st>>>(p);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, st));
+  h->timed = true;
+  if (memspace == TE_HOST) {
+    CU(cudaMemcpyAsync(obs, raw ? (void *)h->d_obs_i : (void *)h->d_obs_f, E * obs_len * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(reward, h->d_reward, E * h->I * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(done, h->d_done, E, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
+                       int memspace, void *stream) {
+  return launch_step(h, actions, k_ticks, 0, obs, reward, done, memspace, stream);
+}
+
+extern "C" int te_step_raw(te_handle *h, const uint8_t *actions, int32_t *obs, float *reward, uint8_t *done,
+                           int memspace, void *stream) {
+  return launch_step(h, actions, 1, 1, obs, reward, done, memspace, stream);
+}
+
+extern "C" int te_remi_reward(te_handle *h, float *reward, int memspace, void *stream) {
+  if (!h || !reward) return fail("te_remi_reward: null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = pick_stream(h, stream);
+  float *dr = memspace == TE_HOST ? h->d_reward : reward;
+  te_remi_kernel<<<h->cfg.num_envs, 128, 0, st>>>(h->base, dr);
+  CU(cudaGetLastError());
+  if (memspace == TE_HOST) {
+    CU(cudaMemcpyAsync(reward, dr, (size_t)h->cfg.num_envs * h->I * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int te_cars_on_roads(te_handle *h, int32_t *out, int memspace, void *stream) {
+  if (!h || !out) return fail("te_cars_on_roads: null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = pick_stream(h, stream);
+  const size_t n = (size_t)h->cfg.num_envs * h->R;
+  int *d = out;
+  if (memspace == TE_HOST) {
+    if (!h->d_cars) CU(dalloc(&h->d_cars, n));
+    d = h->d_cars;
+  }
+  te_cars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->base, d);
+  CU(cudaGetLastError());
+  if (memspace == TE_HOST) {
+    CU(cudaMemcpyAsync(out, d, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int te_greedy_actions(te_handle *h, uint8_t *actions, int memspace, void *stream) {
+  if (!h || !actions) return fail("te_greedy_actions: null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = pick_stream(h, stream);
+  const size_t n = (size_t)h->cfg.num_envs * h->I;
+  uint8_t *d = memspace == TE_HOST ? h->d_actions : actions;
+  te_greedy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->base, d);
+  CU(cudaGetLastError());
+  if (memspace == TE_HOST) {
+    CU(cudaMemcpyAsync(actions, d, n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+extern "C" int te_get_state(te_handle *h, int32_t env_begin, int32_t count, int32_t *leading, int32_t *lastcar, float *x,
+                            float *v, int32_t *obs, int32_t *waiting, uint8_t *passed_dst, float *steps) {
+  if (!h) return fail("te_get_state: null handle");
+  if (env_begin < 0 || count < 0 || env_begin + count > h->cfg.num_envs) return fail("te_get_state: env range out of bounds");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t row = (size_t)h->Rp * CAP;
+  std::vector<float> hx(row * count), hv(row * count);
+  std::vector<int> hel((size_t)h->I * count);
+  std::vector<uint8_t> hph((size_t)h->I * count), hpd((size_t)h->I * count);
+  std::vector<EnvScalars> hes(count);
+  CU(cudaMemcpy(hx.data(), h->x + env_begin * row, hx.size() * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hv.data(), h->v + env_begin * row, hv.size() * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hel.data(), h->elapsed + (size_t)env_begin * h->I, hel.size() * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hph.data(), h->phase + (size_t)env_begin * h->I, hph.size(), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hpd.data(), h->passed_dst + (size_t)env_begin * h->I, hpd.size(), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(hes.data(), h->env + env_begin, hes.size() * sizeof(EnvScalars), cudaMemcpyDeviceToHost));
+  const int R = h->R, r = h->r, I = h->I, ol = 2 * r + 2 * I;
+  for (int e = 0; e < count; e++) {
+    for (int rd = 0; rd < R; rd++) {
+      uint32_t w0; memcpy(&w0, &hx[e * row + (size_t)rd * CAP], 4);
+      int wt; memcpy(&wt, &hv[e * row + (size_t)rd * CAP], 4);
+      if (leading) leading[(size_t)e * R + rd] = w0 & 0xff;
+      if (lastcar) lastcar[(size_t)e * R + rd] = (w0 >> 8) & 0xff;
+      if (obs && rd < r) { obs[(size_t)e * ol + rd] = 0; obs[(size_t)e * ol + r + rd] = (w0 >> 16) & 0xff; }
+      if (waiting && rd < r) waiting[(size_t)e * r + rd] = wt;
+      if (x) { memcpy(&x[((size_t)e * R + rd) * CAP], &hx[e * row + (size_t)rd * CAP], CAP * 4); x[((size_t)e * R + rd) * CAP] = NAN; }
+      if (v) { memcpy(&v[((size_t)e * R + rd) * CAP], &hv[e * row + (size_t)rd * CAP], CAP * 4); v[((size_t)e * R + rd) * CAP] = NAN; }
+    }
+    for (int i = 0; i < I; i++) {
+      if (obs) { obs[(size_t)e * ol + 2 * r + i] = hph[(size_t)e * I + i]; obs[(size_t)e * ol + 2 * r + I + i] = hel[(size_t)e * I + i]; }
+      if (passed_dst) passed_dst[(size_t)e * I + i] = hpd[(size_t)e * I + i];
+    }
+    if (steps) steps[e] = hes[e].steps;
+  }
+  return 0;
+}
+
+extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *leading, const int32_t *lastcar,
+                            const float *x, const float *v, const int32_t *obs, const int32_t *waiting,
+                            const uint8_t *passed_dst, const float *steps) {
+  if (!h) return fail("te_set_state: null handle");
+  if (env_begin < 0 || count < 0 || env_begin + count > h->cfg.num_envs) return fail("te_set_state: env range out of bounds");
+  if (!leading || !lastcar || !x || !v || !obs || !waiting || !passed_dst) return fail("te_set_state: all state arrays are required");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t row = (size_t)h->Rp * CAP;
+  const int R = h->R, r = h->r, I = h->I, ol = 2 * r + 2 * I;
+  std::vector<float> hx(row * count, 0.f), hv(row * count, 0.f);
+  std::vector<int> hel((size_t)I * count);
+  std::vector<uint8_t> hph((size_t)I * count), hpd((size_t)I * count);
+  std::vector<EnvScalars> hes(count);
+  CU(cudaMemcpy(hes.data(), h->env + env_begin, hes.size() * sizeof(EnvScalars), cudaMemcpyDeviceToHost));
+  for (int e = 0; e < count; e++) {
+    for (int rd = 0; rd < h->Rp; rd++) {
+      uint32_t w0 = pack_meta(1, 1, 0); int wt = 0;
+      float *xr = &hx[e * row + (size_t)rd * CAP], *vr = &hv[e * row + (size_t)rd * CAP];
+      if (rd < R) {
+        const int ld = leading[(size_t)e * R + rd], lc = lastcar[(size_t)e * R + rd];
+        if (ld < 1 || ld >= CAP || lc < 1 || lc >= CAP) return fail("te_set_state: ring index out of range");
+        memcpy(xr, &x[((size_t)e * R + rd) * CAP], CAP * 4);
+        memcpy(vr, &v[((size_t)e * R + rd) * CAP], CAP * 4);
+        const int det = rd < r ? obs[(size_t)e * ol + r + rd] : 0;
+        w0 = pack_meta(ld, lc, det);
+        wt = rd < r ? waiting[(size_t)e * r + rd] : 0;
+      } else {
+        xr[1] = INFINITY;
+      }
+      memcpy(xr, &w0, 4); memcpy(vr, &wt, 4);
+    }
+    for (int i = 0; i < I; i++) {
+      hph[(size_t)e * I + i] = obs[(size_t)e * ol + 2 * r + i] != 0;
+      hel[(size_t)e * I + i] = obs[(size_t)e * ol + 2 * r + I + i];
+      hpd[(size_t)e * I + i] = passed_dst[(size_t)e * I + i];
+    }
+    if (steps) hes[e].steps = steps[e];
+  }
+  CU(cudaMemcpy(h->x + env_begin * row, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->v + env_begin * row, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->elapsed + (size_t)env_begin * I, hel.data(), hel.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->phase + (size_t)env_begin * I, hph.data(), hph.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->passed_dst + (size_t)env_begin * I, hpd.data(), hpd.size(), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->env + env_begin, hes.data(), hes.size() * sizeof(EnvScalars), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int te_get_stats(te_handle *h, te_stats *out) {
+  if (!h || !out) return fail("te_get_stats: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  DeviceStats s;
+  CU(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
+  out->ticks = s.ticks; out->actor_steps = s.actor_steps; out->vehicle_updates = s.vehicle_updates;
+  out->overflows = s.overflows; out->cars_generated = s.cars_generated; out->episodes = s.episodes;
+  out->return_sum = s.return_sum; out->disc_return_sum = s.disc_return_sum; out->seq_fallback_ticks = s.seq_fallback_ticks;
+  return 0;
+}
+
+extern "C" int te_get_trip_times(te_handle *h, float *out, int64_t cap, int64_t *count, int clear) {
+  (void)out; (void)cap; (void)clear;
+  if (!h || !count) return fail("te_get_trip_times: null argument");
+  if (!(h->cfg.flags & TE_VALIDATE)) return fail("te_get_trip_times: handle was not created with TE_VALIDATE");
+  return fail("te_get_trip_times: validate mode is not implemented yet");
+}
+
+extern "C" int te_synchronize(te_handle *h) {
+  if (!h) return fail("te_synchronize: null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int te_last_kernel_ms(te_handle *h, float *ms) {
+  if (!h || !ms) return fail("te_last_kernel_ms: null argument");
+  if (!h->timed) return fail("te_last_kernel_ms: no step has been launched");
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return 0;
+}
+
+// ------------------------------------------------------------------ test hooks
+extern "C" int te_test_powf(int device, const float *x, float y, float *out, int64_t n) {
+  CU(cudaSetDevice(device));
+  float *dx = nullptr, *dout = nullptr;
+  CU(cudaMalloc(&dx, n * 4)); CU(cudaMalloc(&dout, n * 4));
+  CU(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  te_test_powf_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, y, dout, n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout, n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout);
+  return 0;
+}
+
+extern "C" int te_test_idm(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
+                           const float *x, const float *v, float *x_out, float *v_out, int64_t n) {
+  CU(cudaSetDevice(device));
+  IdmConst c;
+  c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
+  { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
+  c.len_plus = 0.f;
+  float *d[7];
+  const float *src[5] = {xl, vl, ll, x, v};
+  for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
+  for (int i = 0; i < 5; i++) CU(cudaMemcpy(d[i], src[i], n * 4, cudaMemcpyHostToDevice));
+  te_test_idm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(c, d[0], d[1], d[2], d[3], d[4], d[5], d[6], n);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(x_out, d[5], n * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(v_out, d[6], n * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 7; i++) cudaFree(d[i]);
+  return 0;
+}
+
+extern "C" int te_test_philox(int device, const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+  CU(cudaSetDevice(device));
+  uint32_t *d = nullptr;
+  CU(cudaMalloc(&d, 10 * 4));
+  CU(cudaMemcpy(d, ctr, 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d + 4, key, 8, cudaMemcpyHostToDevice));
+  te_test_philox_kernel<<<1, 1>>>(d, d + 4, d + 6);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d + 6, 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}

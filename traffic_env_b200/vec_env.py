@@ -1,0 +1,216 @@
+"""VecTrafficEnv: E independent traffic-env instances advanced by one CUDA kernel launch.
+
+Host-side mirror of the reference's TrafficEnv (gym_traffic/envs/traffic_env.py:221-394)
+plus the Repeater/Remi wrappers that sit on its tick loop (traffic_test.py:27-64), for a
+batch of env instances.  All simulation work happens in libtraffic_b200.so (sm_100a CUDA,
+C ABI in include/traffic_b200.h); this class only marshals buffers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (TE_ARRIVALS_INJECTED, TE_ARRIVALS_NONE, TE_ARRIVALS_PHILOX, TE_AUTO_RESET, TE_CAP, TE_DEVICE,
+                   TE_HOST, TE_LEARN_SWITCH, TE_REMI, TE_VALIDATE, check)
+
+ARCHETYPE = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], dtype=np.float32)  # traffic_env.py:35-43
+
+
+def inv_popcount(spec):
+    """Open sides of the grid (traffic_env.py:180-185: popcount of the inverted low 4 bits)."""
+    return bin((~int(spec)) & 0b1111).count("1")
+
+
+def entry_spec_of(entry):
+    if isinstance(entry, str):
+        if entry == "all":
+            return 0
+        if entry == "one":
+            return 0b1110  # traffic_env.py:391
+        raise ValueError("entry must be 'all', 'one' or an integer side mask")
+    return int(entry)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())  # torch tensor
+
+
+class VecTrafficEnv(object):
+    def __init__(self, m=3, n=3, length=250.0, num_envs=1, rate=0.5, ticks_per_step=10, remi=True,
+                 learn_switch=False, auto_reset=False, validate=False, arrivals="philox", local_cars_per_sec=0.12,
+                 entry="all", seed=0, env_id_base=0, device=0, episode_len=0, gamma=0.8, archetype=None):
+        L = _lib.load()
+        cfg = _lib.default_config()
+        cfg.m, cfg.n, cfg.length, cfg.rate = int(m), int(n), float(length), float(rate)
+        cfg.num_envs, cfg.env_id_base, cfg.device = int(num_envs), int(env_id_base), int(device)
+        cfg.flags = ((TE_REMI if remi else 0) | (TE_LEARN_SWITCH if learn_switch else 0) |
+                     (TE_AUTO_RESET if auto_reset else 0) | (TE_VALIDATE if validate else 0))
+        cfg.entry_spec = entry_spec_of(entry)
+        cfg.arrival_mode = {"philox": TE_ARRIVALS_PHILOX, "injected": TE_ARRIVALS_INJECTED,
+                            "none": TE_ARRIVALS_NONE}[arrivals]
+        # FLAGS.cars_per_sec = local_cars_per_sec * m * inv_popcount(spec)  (traffic_env.py:394)
+        self.cars_per_sec = float(local_cars_per_sec) * int(m) * inv_popcount(cfg.entry_spec)
+        cfg.cars_per_tick = self.cars_per_sec * float(rate)
+        cfg.seed, cfg.episode_len, cfg.gamma = int(seed), int(episode_len), float(gamma)
+        arch = ARCHETYPE if archetype is None else np.asarray(archetype, dtype=np.float32)
+        for i in range(_lib.TE_PARAMS):
+            cfg.archetype[i] = float(arch[i])
+        self._L = L
+        self._h = C.c_void_p()
+        check(L.te_create(C.byref(cfg), C.byref(self._h)))
+        d = _lib.TeDims()
+        check(L.te_get_dims(self._h, C.byref(d)))
+        self.m, self.n = d.m, d.n
+        self.intersections, self.train_roads, self.roads = d.intersections, d.train_roads, d.roads
+        self.num_envs, self.num_entry = d.num_envs, d.num_entry
+        self.obs_raw_len, self.obs_len = d.obs_raw, d.obs_actor
+        self.ticks_per_step = int(ticks_per_step)
+        self.device = int(device)
+        self.remi = bool(remi)
+        self.dest = np.empty(self.roads, np.int32)
+        self.nexts = np.empty(self.roads, np.int32)
+        self.phases = np.empty(self.roads, np.int32)
+        self.entrypoints = np.empty(self.num_entry, np.int32)
+        check(L.te_get_topology(self._h, self.dest.ctypes.data, self.nexts.ctypes.data, self.phases.ctypes.data,
+                                self.entrypoints.ctypes.data))
+        E, I = self.num_envs, self.intersections
+        self._obs = np.empty((E, self.obs_len), np.float32)
+        self._obs_raw = np.empty((E, self.obs_raw_len), np.int32)
+        self._reward = np.empty((E, I), np.float32)
+        self._done = np.empty(E, np.uint8)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.te_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------ helpers
+    def _actions(self, actions):
+        a = np.asarray(actions)
+        a = np.ascontiguousarray(a.astype(bool).reshape(self.num_envs, self.intersections), dtype=np.uint8)
+        return a
+
+    # ------------------------------------------------------------ reference API, batched
+    def reset(self, mask=None, init_phase=None):
+        """TrafficEnv._reset for the masked envs (all when mask is None)."""
+        mk = None if mask is None else np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        ip = None if init_phase is None else np.ascontiguousarray(
+            np.asarray(init_phase).astype(bool).reshape(self.num_envs, self.intersections), dtype=np.uint8)
+        check(self._L.te_reset(self._h, _ptr(mk), _ptr(ip), TE_HOST, None))
+
+    def set_arrivals(self, schedules):
+        """schedules[e][t] = ordered entry-road ids of env e at schedule tick t."""
+        E = self.num_envs
+        assert len(schedules) == E
+        horizon = max(len(s) for s in schedules)
+        off = np.zeros((E, horizon + 1), dtype=np.int64)
+        roads = []
+        base = 0
+        for e, s in enumerate(schedules):
+            off[e, 0] = base
+            for t in range(horizon):
+                if t < len(s):
+                    roads.extend(int(x) for x in s[t])
+                    base += len(s[t])
+                off[e, t + 1] = base
+        roads = np.asarray(roads, dtype=np.int16)
+        self.set_arrivals_csr(off, roads, horizon)
+
+    def set_arrivals_csr(self, offsets, roads, horizon):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        roads = np.ascontiguousarray(roads, dtype=np.int16)
+        assert offsets.size == self.num_envs * (horizon + 1)
+        if roads.size == 0:
+            roads = np.zeros(1, np.int16)
+        check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(horizon)))
+
+    def step(self, actions, k=None):
+        """One actor step (Repeater(k) [+ Remi]) for every env; returns (obs, reward, done) host arrays
+        that are reused between calls, like the reference's in-place obs/rewards buffers."""
+        a = self._actions(actions)
+        k = self.ticks_per_step if k is None else int(k)
+        check(self._L.te_step(self._h, a.ctypes.data, k, self._obs.ctypes.data, self._reward.ctypes.data,
+                              self._done.ctypes.data, TE_HOST, None))
+        return self._obs, self._reward, self._done
+
+    def step_raw(self, actions):
+        """One physics tick (bare TrafficEnv._step); obs is int32 passed|detected|phase|elapsed."""
+        a = self._actions(actions)
+        check(self._L.te_step_raw(self._h, a.ctypes.data, self._obs_raw.ctypes.data, self._reward.ctypes.data,
+                                  self._done.ctypes.data, TE_HOST, None))
+        return self._obs_raw, self._reward, self._done
+
+    def step_device(self, actions, obs, reward, done, k=None, stream=None):
+        """Same as step() on caller-owned device buffers (torch CUDA tensors or raw pointers); asynchronous."""
+        k = self.ticks_per_step if k is None else int(k)
+        check(self._L.te_step(self._h, _ptr(actions), k, _ptr(obs), _ptr(reward), _ptr(done), TE_DEVICE, stream))
+
+    def step_pinned(self, actions, obs, reward, done, k=None):
+        """step() on caller-owned HOST buffers (e.g. pinned torch tensors); synchronous."""
+        k = self.ticks_per_step if k is None else int(k)
+        check(self._L.te_step(self._h, _ptr(actions), k, _ptr(obs), _ptr(reward), _ptr(done), TE_HOST, None))
+
+    def remi_reward(self):
+        out = np.empty((self.num_envs, self.intersections), np.float32)
+        check(self._L.te_remi_reward(self._h, out.ctypes.data, TE_HOST, None))
+        return out
+
+    def cars_on_roads_flat(self):
+        out = np.empty((self.num_envs, self.roads), np.int32)
+        check(self._L.te_cars_on_roads(self._h, out.ctypes.data, TE_HOST, None))
+        return out
+
+    def cars_on_roads(self):
+        """[E, m, n, 4] like TrafficEnv.cars_on_roads (traffic_env.py:255-257)."""
+        c = self.cars_on_roads_flat()[:, :self.train_roads]
+        return np.transpose(c.reshape(self.num_envs, 4, self.m, self.n), (0, 2, 3, 1))
+
+    def greedy_actions(self, out=None):
+        if out is None:
+            out = np.empty((self.num_envs, self.intersections), np.uint8)
+            check(self._L.te_greedy_actions(self._h, out.ctypes.data, TE_HOST, None))
+            return out
+        check(self._L.te_greedy_actions(self._h, _ptr(out), TE_DEVICE, None))
+        return out
+
+    # ------------------------------------------------------------ state / stats
+    def get_state(self, env_begin=0, count=None):
+        count = self.num_envs - env_begin if count is None else count
+        R, r, I = self.roads, self.train_roads, self.intersections
+        st = dict(leading=np.empty((count, R), np.int32), lastcar=np.empty((count, R), np.int32),
+                  x=np.empty((count, R, TE_CAP), np.float32), v=np.empty((count, R, TE_CAP), np.float32),
+                  obs=np.empty((count, 2 * r + 2 * I), np.int32), waiting=np.empty((count, r), np.int32),
+                  passed_dst=np.empty((count, I), np.uint8), steps=np.empty(count, np.float32))
+        check(self._L.te_get_state(self._h, env_begin, count, *[st[k].ctypes.data for k in
+                                   ("leading", "lastcar", "x", "v", "obs", "waiting", "passed_dst", "steps")]))
+        return st
+
+    def set_state(self, st, env_begin=0):
+        count = st["leading"].shape[0]
+        arrs = [np.ascontiguousarray(st[k], dtype=dt) for k, dt in
+                (("leading", np.int32), ("lastcar", np.int32), ("x", np.float32), ("v", np.float32),
+                 ("obs", np.int32), ("waiting", np.int32), ("passed_dst", np.uint8), ("steps", np.float32))]
+        check(self._L.te_set_state(self._h, env_begin, count, *[a.ctypes.data for a in arrs]))
+
+    def stats(self):
+        s = _lib.TeStats()
+        check(self._L.te_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(self._L.te_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self._L.te_synchronize(self._h))
