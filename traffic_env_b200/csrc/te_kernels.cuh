@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     const int el_f = ls_act ? 0 : s.elapsed[i] + last;
     p.phase[(size_t)env * p.I + i] = (uint8_t)ph_f;
     p.elapsed[(size_t)env * p.I + i] = el_f;
-    float rew = __fmul_rn(-10.0f, (float)s.ovf[i]);  // OVERFLOW_PENALTY, summed over the ticks (exact)
+    float rew = (float)(-10 * s.ovf[i]);  // OVERFLOW_PENALTY summed over the ticks: small integers, exact, +0 when none
     if (!p.raw && (p.flags & F_REMI)) {
       // remi, traffic_env.py:64-78, over the 4 approaches of intersection i in road order
       rew = 0.f;
