@@ -145,7 +145,7 @@ int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *
                  const float *x, const float *v, const int32_t *obs, const int32_t *waiting,
                  const uint8_t *passed_dst, const float *steps);
 
-/* Counters since te_create (device -> host; synchronises the handle's stream). */
+/* Counters since te_create (device -> host; synchronises the device). */
 int te_get_stats(te_handle *h, te_stats *out);
 
 /* Trip times recorded in validate mode (traffic_env.py:154), seconds; returns the number available

@@ -435,7 +435,7 @@ extern "C" int te_get_state(te_handle *h, int32_t env_begin, int32_t count, int3
   if (!h) return fail("te_get_state: null handle");
   if (env_begin < 0 || count < 0 || env_begin + count > h->cfg.num_envs) return fail("te_get_state: env range out of bounds");
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaDeviceSynchronize());
   const size_t row = (size_t)h->Rp * CAP;
   std::vector<float> hx(row * count), hv(row * count);
   std::vector<int> hel((size_t)h->I * count);
@@ -475,7 +475,7 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
   if (env_begin < 0 || count < 0 || env_begin + count > h->cfg.num_envs) return fail("te_set_state: env range out of bounds");
   if (!leading || !lastcar || !x || !v || !obs || !waiting || !passed_dst) return fail("te_set_state: all state arrays are required");
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaDeviceSynchronize());
   const size_t row = (size_t)h->Rp * CAP;
   const int R = h->R, r = h->r, I = h->I, ol = 2 * r + 2 * I;
   std::vector<float> hx(row * count, 0.f), hv(row * count, 0.f);
@@ -519,7 +519,7 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
 extern "C" int te_get_stats(te_handle *h, te_stats *out) {
   if (!h || !out) return fail("te_get_stats: null argument");
   CU(cudaSetDevice(h->device));
-  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaDeviceSynchronize());  // steps may have been queued on caller-provided streams
   DeviceStats s;
   CU(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
   out->ticks = s.ticks; out->actor_steps = s.actor_steps; out->vehicle_updates = s.vehicle_updates;

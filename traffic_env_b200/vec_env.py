@@ -175,12 +175,13 @@ class VecTrafficEnv(object):
         c = self.cars_on_roads_flat()[:, :self.train_roads]
         return np.transpose(c.reshape(self.num_envs, 4, self.m, self.n), (0, 2, 3, 1))
 
-    def greedy_actions(self, out=None):
+    def greedy_actions(self, out=None, stream=None):
+        """algorithms/greedy.py:14-16 for every env; host array by default, or into a device buffer `out`."""
         if out is None:
             out = np.empty((self.num_envs, self.intersections), np.uint8)
             check(self._L.te_greedy_actions(self._h, out.ctypes.data, TE_HOST, None))
             return out
-        check(self._L.te_greedy_actions(self._h, _ptr(out), TE_DEVICE, None))
+        check(self._L.te_greedy_actions(self._h, _ptr(out), TE_DEVICE, stream))
         return out
 
     # ------------------------------------------------------------ state / stats
