@@ -150,7 +150,6 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->V = m * n; h->I = h->V; h->r = 4 * h->V; h->R = h->r + 2 * n + 2 * m;
   h->Rp = (h->R + GROUP_ROADS - 1) / GROUP_ROADS * GROUP_ROADS;
   h->G = h->Rp / GROUP_ROADS;
-  if (h->Rp > 32000) { free_handle(h); return fail("te_create: grid too large"); }
   // topology (roadgraph.py:35-39, 42-51)
   h->dest.resize(h->R); h->nexts.resize(h->R); h->phases.resize(h->R);
   std::vector<short> nx(h->Rp, -1), up(h->Rp, -1);
@@ -231,23 +230,14 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
   p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0;
 
-  // warps per CTA: enough to cover the road groups in few balanced rounds
-  int warps = h->G <= 16 ? h->G : 0;
-  if (!warps) {
-    int best = 16, best_waste = 1 << 30;
-    for (int w = 16; w >= 8; w--) {
-      const int rounds = (h->G + w - 1) / w, waste = rounds * w - h->G;
-      if (waste < best_waste) { best_waste = waste; best = w; }
-    }
-    warps = best;
-  }
-  if (warps < 2) warps = 2;
-  if (const char *ev = getenv("TE_WARPS")) { const int w = atoi(ev); if (w >= 1 && w <= MAX_THREADS / 32) warps = w; }
-  h->warps = warps;
+  // one thread per (padded) road: warp w owns roads [32w, 32w + 32)
+  h->warps = h->Rp / GROUP_ROADS;
+  if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
   CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry);
   if (L.total > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", L.total, h->smem_optin); }
-  CUH(cudaFuncSetAttribute(te_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUH(cudaFuncSetAttribute(te_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUH(cudaFuncSetAttribute(te_step_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
   te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
@@ -359,7 +349,8 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
   }
   const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry);
   CU(cudaEventRecord(h->ev0, st));
-  te_step_kernel<<<h->cfg.num_envs, h->warps * 32, L.total, st>>>(p);
+  if (h->Rp <= 512) te_step_kernel<512><<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
+  else te_step_kernel<1024><<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;

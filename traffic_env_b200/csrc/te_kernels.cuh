@@ -6,15 +6,21 @@
 // as two float planes x[Rp][20], v[Rp][20] - every car has the same archetype
 // (traffic_env.py:35-43), so x and v are the only dynamic fields - and flushed once.
 //
+// Roads map to warps: warp w owns roads [32w, 32w+32), lane = road, for the whole launch; the
+// road's ring indices and counters live in that lane's registers.
+//
 // Per tick (order of traffic_env.py:224-248, see DESIGN.md "tick phases"):
-//   phase A  (a warp owns groups of 8 roads = 160 ring slots = 5 lane-passes)
-//     - entry arrivals -> add_car                              (traffic_env.py:274-283, 97-114)
-//     - virtual leader x from the light state                  (update_lights, :81-94)
-//     - slot 0 <- slot 19 mirror, then Jacobi IDM update of every live slot from its
-//       predecessor slot (sim, :50-62; move_cars, :187-212), waiting/detected counts
-//     - pops: leading advances past cars with x > length        (advance_finished_cars, :117-135)
+//   phase A  (warp-local, no CTA barrier inside)
+//     - lane = road: entry arrivals -> add_car                 (traffic_env.py:274-283, 97-114)
+//     - lane = road: virtual leader x from the light state     (update_lights, :81-94)
+//     - the warp's live cars are compacted into lanes in ring order (warp prefix sum over the
+//       per-road counts + a per-warp item list), 32 cars per chunk, every lane busy; each car
+//       reads its predecessor's pre-update (x, v) - chunks run back to front so the in-place
+//       update is the Jacobi update of sim (:50-62) / move_cars (:187-212); waiting/detected
+//       counts come back to the road lanes through ballots
+//     - lane = road: pops - leading advances past cars with x > length (advance_finished_cars, :117-135)
 //   barrier
-//   phase C  (a thread owns a destination road)
+//   phase C  (lane = destination road)
 //     - popped cars of the unique upstream road are inserted with add_car semantics;
 //       whether the insert sees the destination's pre- or post-pop `leading` follows the
 //       reference's road-index order (upstream < dest: pre-pop)
@@ -30,8 +36,8 @@ namespace te {
 constexpr int CAP = 20;            // CAPACITY, traffic_env.py:24
 constexpr int RING = CAP - 1;      // live ring positions 1..19
 constexpr int YELLOW_TICKS = 6;    // traffic_env.py:21
-constexpr int GROUP_ROADS = 8;     // 8 roads * 20 slots = 160 = 5 * 32 lanes
-constexpr int GROUP_PASSES = 5;
+constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
+constexpr int WARP_ITEMS = 640;    // per-warp compaction list: 32 roads * 18 cars = 576 entries, padded
 constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8 };
@@ -93,7 +99,7 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 }
 
 struct SmemLayout {
-  int xs, vs, leadx, tailx, meta, wait, pd, nexts, up, eidx, phase, act, pdst, elapsed, ovf, cnt, snap, tabs, misc, total;
+  int xs, vs, tabs, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
 };
 
 __host__ __device__ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -104,18 +110,14 @@ __host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_en
   L.xs = o; o += Rp * CAP * 4;
   L.vs = o; o += Rp * CAP * 4;
   L.tabs = o; o += (int)sizeof(PowfTables);            // 512 B, 8-aligned
-  L.leadx = o; o += Rp * 4;
   L.tailx = o; o += Rp * 4;
   L.meta = o; o += Rp * 4;
   L.wait = o; o += Rp * 4;
-  L.pd = o; o += Rp * 4;                               // passed_acc | detected << 16
   L.elapsed = o; o += align_up(I, 4) * 4;
   L.ovf = o; o += align_up(I, 4) * 4;
   L.snap = o; o += (MAX_K + 1) * 8;                    // Philox (draw, skip) before each tick
   L.misc = o; o += 32;
-  L.nexts = o; o += Rp * 2;
-  L.up = o; o += Rp * 2;
-  L.eidx = o; o += Rp;
+  L.items = o; o += (Rp / GROUP_ROADS) * WARP_ITEMS;
   L.phase = o; o += align_up(I, 4);
   L.act = o; o += align_up(I, 4);
   L.pdst = o; o += align_up(I, 4);
@@ -142,62 +144,50 @@ __device__ __forceinline__ bool ring_push(float *xr, float *vr, int chk, int &lc
 }
 
 struct Smem {
-  float *xs, *vs, *leadx, *tailx;
-  uint32_t *meta;        // leading | lastcar << 8 | pre-pop leading << 16 | npop << 24
-  int *wait, *pd, *elapsed, *ovf;
+  float *xs, *vs, *tailx;
+  uint32_t *meta;        // published after phase A: leading | lastcar << 8 | pre-pop leading << 16 | npop << 24
+  int *wait, *elapsed, *ovf;
   uint32_t *snap;
   int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks
-  short *nexts, *up;
-  signed char *eidx;
-  uint8_t *phase, *act, *pdst, *cnt;
+  uint8_t *items, *phase, *act, *pdst, *cnt;
   PowfTables *tabs;
 };
 
 __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) {
   Smem s;
-  s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs);
-  s.leadx = (float *)(base + L.leadx); s.tailx = (float *)(base + L.tailx);
-  s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait); s.pd = (int *)(base + L.pd);
+  s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs); s.tailx = (float *)(base + L.tailx);
+  s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
-  s.misc = (int *)(base + L.misc); s.nexts = (short *)(base + L.nexts); s.up = (short *)(base + L.up);
-  s.eidx = (signed char *)(base + L.eidx); s.phase = base + L.phase; s.act = base + L.act;
+  s.misc = (int *)(base + L.misc); s.items = base + L.items; s.phase = base + L.phase; s.act = base + L.act;
   s.pdst = base + L.pdst; s.cnt = base + L.cnt; s.tabs = (PowfTables *)(base + L.tabs);
   return s;
 }
 
 // Move the popped cars of road u to the tail of road d (advance_finished_cars -> add_car,
-// traffic_env.py:126-132).  u < d: the reference inserts before d's own pops of this tick.
-__device__ __forceinline__ void transfer(const StepParams &p, const Smem &s, int u, int d, int t) {
+// traffic_env.py:126-132).  `chk` is the value of leading[d] the reference sees at that moment:
+// the pre-pop value when u < d (the reference inserts before d's own pops of this tick).
+// Returns the number of cars dropped on a full ring.
+__device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int u, int d, int chk, int &dlc) {
   const uint32_t mu = s.meta[u];
   const int np = mu >> 24;
-  if (np == 0) return;
-  const uint32_t md = s.meta[d];
-  const int dld = md & 0xff, dlp = (md >> 16) & 0xff;
-  int dlc = (md >> 8) & 0xff;
-  const int chk = (u < d) ? dlp : dld;
-  int slot = (mu >> 16) & 0xff;
+  int slot = (mu >> 16) & 0xff, dropped = 0;
   float *xd = s.xs + d * CAP, *vd = s.vs + d * CAP;
   for (int k = 0; k < np; k++) {
     slot = ring_wrap(slot + 1);
     const float xin = __fsub_rn(s.xs[u * CAP + slot], p.length);
     const float vin = s.vs[u * CAP + slot];
-    if (!ring_push(xd, vd, chk, dlc, xin, vin, p.idm)) {
-      if (d < p.r) atomicAdd(&s.ovf[d % p.V], 1);
-      atomicAdd(&s.misc[3], 1);
-      atomicMin(&s.misc[0], t);
-    }
+    if (!ring_push(xd, vd, chk, dlc, xin, vin, p.idm)) dropped++;
   }
-  s.meta[d] = (md & 0xffff00ffu) | ((uint32_t)dlc << 8);
+  return dropped;
 }
 
-constexpr int MAX_THREADS = 512;
-
-__global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry);
   const Smem s = carve(smem_raw, L);
   const int env = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned FULL = 0xffffffffu;
   const float INF = __int_as_float(0x7f800000);
   const bool learn_switch = (p.flags & F_LEARN_SWITCH) != 0;
@@ -211,14 +201,11 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     const int n4 = p.Rp * (CAP / 4);
     for (int i = tid; i < n4; i += blockDim.x) { sx[i] = gx[i]; sv[i] = gv[i]; }
   }
-  for (int i = tid; i < p.Rp; i += blockDim.x) {
-    s.nexts[i] = p.nexts[i]; s.up[i] = p.up[i]; s.eidx[i] = p.entry_idx[i];
-  }
-  if (tid < 64) reinterpret_cast<unsigned long long *>(s.tabs)[tid] =
-      reinterpret_cast<const unsigned long long *>(&g_powf_tables)[tid];
+  for (int i = tid; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long *>(s.tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
   for (int i = tid; i < p.I; i += blockDim.x) {
     // phase / elapsed update of the first tick (traffic_env.py:225-232); later ticks of the same
-    // actor step repeat the same action and are derived in closed form (phase_at / elapsed_at).
+    // actor step repeat the same action and are derived in closed form below.
     int ph = p.phase[(size_t)env * p.I + i] != 0;
     const int act = p.actions[(size_t)env * p.I + i] != 0;
     int el = p.elapsed[(size_t)env * p.I + i];
@@ -266,15 +253,24 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     }
   }
   __syncthreads();
-  for (int road = tid; road < p.Rp; road += blockDim.x) {
-    const uint32_t w0 = __float_as_uint(s.xs[road * CAP]);
-    const int ld = w0 & 0xff, lc = (w0 >> 8) & 0xff, det = (w0 >> 16) & 0xff;
-    s.meta[road] = (uint32_t)ld | ((uint32_t)lc << 8) | ((uint32_t)ld << 16);
-    s.wait[road] = __float_as_int(s.vs[road * CAP]);
-    s.pd[road] = det << 16;
-    s.leadx[road] = s.xs[road * CAP + ld];
-    s.tailx[road] = (lc != ld) ? s.xs[road * CAP + lc] : INF;
+
+  // ---- lane = road: ring indices, counters and topology of my road live in registers
+  const int my_road = tid;                       // blockDim.x == Rp
+  const bool is_road = my_road < p.R, is_train = my_road < p.r;
+  float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
+  int ld, lc, wait, det, passed = 0;
+  float leadx;
+  {
+    const uint32_t w0 = __float_as_uint(xr[0]);
+    ld = w0 & 0xff; lc = (w0 >> 8) & 0xff; det = (w0 >> 16) & 0xff;
+    wait = __float_as_int(vr[0]);
+    leadx = xr[ld];
+    s.tailx[my_road] = (lc != ld) ? xr[lc] : INF;
   }
+  const int nxt = p.nexts[my_road], upr = p.up[my_road], ei = p.entry_idx[my_road];
+  const int dst = is_train ? my_road % p.V : 0;
+  const int road_phase = (my_road / p.V) < 2;
+  uint8_t *items = s.items + warp * WARP_ITEMS;
   __syncthreads();
 
   const IdmConst c = p.idm;
@@ -282,134 +278,119 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
   int t = 0;
   for (; t < p.K; t++) {
     // ---------------------------------------------------------------- phase A
-    for (int g = warp; g < p.G; g += nwarps) {
-      const int my_road = g * GROUP_ROADS + lane;  // per-road bookkeeping lane (lanes 0..7)
-      const bool road_lane = lane < GROUP_ROADS && my_road < p.R;
-      if (road_lane) {
-        const uint32_t m = s.meta[my_road];
-        const int ld = m & 0xff;
-        int lc = (m >> 8) & 0xff;
-        float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
-        const int ei = s.eidx[my_road];
-        if (ei >= 0) {
-          const int na = s.cnt[t * p.n_entry + ei];
-          for (int k = 0; k < na; k++) {
-            gen_local++;
-            if (!ring_push(xr, vr, ld, lc, c.x_new, c.v_new, c)) {
-              if (my_road < p.r) atomicAdd(&s.ovf[my_road % p.V], 1);
-              atomicAdd(&s.misc[3], 1);
-              atomicMin(&s.misc[0], t);
-            }
-          }
-          s.meta[my_road] = (m & 0xffff00ffu) | ((uint32_t)lc << 8);
-        }
-        if (my_road < p.r) {  // update_lights, traffic_env.py:81-94
-          const int dst = my_road % p.V;
-          const bool ls_act = learn_switch && s.act[dst];
-          const int ph_t = s.phase[dst] ^ (ls_act ? (t & 1) : 0);
-          const int el_t = ls_act ? 0 : s.elapsed[dst] + t;
-          const int road_phase = (my_road / p.V) < 2;
-          float lx;
-          if (road_phase == ph_t || el_t < YELLOW_TICKS) lx = p.length;
-          else { const int nr = s.nexts[my_road]; lx = nr >= 0 ? __fadd_rn(s.tailx[nr], p.length) : INF; }
-          s.leadx[my_road] = lx;
-        }
-        xr[0] = xr[CAP - 1]; vr[0] = vr[CAP - 1];  // mirror, traffic_env.py:203
-      }
-      __syncwarp();
-      uint32_t accw = 0, accd = 0, accp = 0;
-#pragma unroll 1
-      for (int pass = GROUP_PASSES - 1; pass >= 0; --pass) {
-        const int f = pass * 32 + lane;
-        const int rl = f / CAP, slot = f - rl * CAP;
-        const int road = g * GROUP_ROADS + rl;
-        const uint32_t m = s.meta[road];
-        const int ld = m & 0xff, lc = (m >> 8) & 0xff;
-        const bool live = slot >= 1 && (ld < lc ? (slot > ld && slot <= lc) : (ld > lc && (slot > ld || slot <= lc)));
-        float xn = 0.f, vn = 0.f;
-        bool pw = false, pdet = false, pp = false;
-        const int o = road * CAP + slot;
-        if (live) {
-          float x = s.xs[o], v = s.vs[o];
-          const bool first = (slot == 1) ? (ld == CAP - 1) : (slot - 1 == ld);
-          const float xl = first ? s.leadx[road] : s.xs[o - 1];
-          const float vl = first ? 0.f : s.vs[o - 1];
-          const float ll = first ? 0.f : c.len;
-          idm_update(c, s.tabs, xl, vl, ll, x, v);
-          xn = x; vn = v;
-          // wrapped ring, low segment: the reference tests x, not v (traffic_env.py:210)
-          const bool lowseg = ld > lc && slot <= lc;
-          pw = (double)(lowseg ? xn : vn) < 0.2;
-          pdet = (double)xn > p.det_thr;
-          pp = xn > p.length;
-        }
-        const uint32_t bw = __ballot_sync(FULL, pw), bd = __ballot_sync(FULL, pdet), bp = __ballot_sync(FULL, pp);
-        __syncwarp();  // every lane has read its leader before any lane overwrites a slot (Jacobi update)
-        if (live) { s.xs[o] = xn; s.vs[o] = vn; }
-        if (lane < GROUP_ROADS) {
-          const int base = CAP * lane - 32 * pass;  // bit position of my road's slot 0 in this pass
-          if (base < 32 && base > -CAP) {
-            const uint32_t mask = (1u << CAP) - 1;
-            accw |= (base >= 0 ? bw >> base : bw << -base) & mask;
-            accd |= (base >= 0 ? bd >> base : bd << -base) & mask;
-            accp |= (base >= 0 ? bp >> base : bp << -base) & mask;
-          }
-        }
-      }
-      __syncwarp();
-      if (road_lane) {
-        const uint32_t m = s.meta[my_road];
-        const int ld = m & 0xff, lc = (m >> 8) & 0xff;
-        const int n = ring_count(ld, lc);
-        int newld = ld, npop = 0;
-        if (n > 0) {
-          veh_local += n;
-          if (my_road < p.r) {
-            s.wait[my_road] += __popc(accw);
-            s.pd[my_road] = (s.pd[my_road] & 0xffff) | (__popc(accd) << 16);
-          }
-          const uint32_t q = (accp >> 1) & 0x7ffffu;   // bit i <-> slot i + 1
-          const int sh = ring_wrap(ld + 1) - 1;
-          const uint32_t rot = ((q >> sh) | (q << (RING - sh))) & 0x7ffffu;
-          npop = __ffs(~rot) - 1;                       // leading run of cars past the end of the road
-          if (npop > 0) {
-            newld = (ld - 1 + npop) % RING + 1;
-            const int nr = s.nexts[my_road];
-            if (nr >= 0) {
-              s.pd[my_road] += npop;                    // passed, traffic_env.py:127
-              s.pdst[my_road % p.V] = 1;                // passed_dst, :128
-              // Two or more pops while the upstream road has a higher index: its insert (which in the
-              // reference runs after these pops were consumed) could reuse the slots the popped cars
-              // still occupy.  Run this tick's transfers in strict road order instead.
-              if (npop >= 2 && s.up[my_road] > my_road) s.misc[1] = t;
-            }
-          }
-        }
-        s.meta[my_road] = (uint32_t)newld | ((uint32_t)lc << 8) | ((uint32_t)ld << 16) | ((uint32_t)npop << 24);
+    int dropped = 0;
+    if (ei >= 0) {  // entry arrivals, traffic_env.py:274-283
+      const int na = s.cnt[t * p.n_entry + ei];
+      for (int k = 0; k < na; k++) {
+        gen_local++;
+        if (!ring_push(xr, vr, ld, lc, c.x_new, c.v_new, c)) dropped++;
       }
     }
+    if (is_train) {  // update_lights, traffic_env.py:81-94
+      const bool ls_act = learn_switch && s.act[dst];
+      const int ph_t = s.phase[dst] ^ (ls_act ? (t & 1) : 0);
+      const int el_t = ls_act ? 0 : s.elapsed[dst] + t;
+      if (road_phase == ph_t || el_t < YELLOW_TICKS) leadx = p.length;
+      else leadx = nxt >= 0 ? __fadd_rn(s.tailx[nxt], p.length) : INF;
+    }
+    const int n = ring_count(ld, lc);
+    // compaction: exclusive prefix sum of the per-road car counts over the warp
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+    const int start = incl - n;
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int k = 0; k < n; k++) items[start + k] = (uint8_t)lane;
+    __syncwarp();
+    int wacc = 0, dacc = 0;
+    for (int ch = (total + 31) / 32 - 1; ch >= 0; --ch) {
+      const int ci = ch * 32 + lane;
+      const bool valid = ci < total;
+      const int j = valid ? items[ci] : 0;                 // owning road lane
+      const int ldj = __shfl_sync(FULL, ld, j), lcj = __shfl_sync(FULL, lc, j);
+      const int k = ci - __shfl_sync(FULL, start, j);      // k-th car from the front of its road
+      const float lxj = __shfl_sync(FULL, leadx, j);
+      float xn = 0.f, vn = 0.f;
+      bool pw = false, pdet = false;
+      int o = 0;
+      if (valid) {
+        const int tt = ldj + k;
+        const int slot = tt < RING ? tt + 1 : tt - (RING - 1);   // ((ld + k) mod 19) + 1
+        const int rbase = (warp * GROUP_ROADS + j) * CAP;
+        o = rbase + slot;
+        float x = s.xs[o], v = s.vs[o];
+        float xl = lxj, vl = 0.f, ll = 0.f;                  // virtual leader: v = 0, l = 0
+        if (k > 0) { const int lo = rbase + (slot == 1 ? RING : slot - 1); xl = s.xs[lo]; vl = s.vs[lo]; ll = c.len; }
+        idm_update(c, s.tabs, xl, vl, ll, x, v);
+        xn = x; vn = v;
+        // wrapped ring, low segment: the reference tests x, not v (traffic_env.py:210)
+        const bool lowseg = ldj > lcj && slot <= lcj;
+        pw = (double)(lowseg ? xn : vn) < 0.2;
+        pdet = (double)xn > p.det_thr;
+      }
+      const uint32_t bw = __ballot_sync(FULL, pw), bd = __ballot_sync(FULL, pdet);
+      __syncwarp();  // every lane has read its leader before any lane overwrites a slot (Jacobi update)
+      if (valid) { s.xs[o] = xn; s.vs[o] = vn; }
+      // my road's cars sit in lanes [lo, hi) of this chunk
+      const int lo = max(start - ch * 32, 0), hi = min(start + n - ch * 32, 32);
+      if (lo < hi) {
+        const uint32_t mask = (hi == 32 ? FULL : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+        wacc += __popc(bw & mask); dacc += __popc(bd & mask);
+      }
+    }
+    __syncwarp();
+    int npop = 0;
+    const int ld_pre = ld;
+    if (n > 0) {
+      veh_local += n;
+      if (is_train) { wait += wacc; det = dacc; }   // detected is only rewritten for non-empty roads (:194)
+      // advance_finished_cars, traffic_env.py:123: pop while the front car is past the end of the road
+      int f = ld;
+      while (npop < n) {
+        const int f2 = ring_wrap(f + 1);
+        if (!(xr[f2] > p.length)) break;
+        f = f2; npop++;
+      }
+      if (npop > 0) {
+        ld = f;
+        if (nxt >= 0) {
+          passed += npop;                               // traffic_env.py:127
+          s.pdst[dst] = 1;                              // :128
+          // Two or more pops while the upstream road has a higher index: its insert (which in the
+          // reference runs after these pops were consumed) could reuse the slots the popped cars
+          // still occupy.  Run this tick's transfers in strict road order instead.
+          if (npop >= 2 && upr > my_road) s.misc[1] = t;
+        }
+      }
+    }
+    s.meta[my_road] = (uint32_t)ld | ((uint32_t)lc << 8) | ((uint32_t)ld_pre << 16) | ((uint32_t)npop << 24);
     __syncthreads();
     // ---------------------------------------------------------------- phase C
     if (s.misc[1] == t) {
       if (tid == 0) {
-        for (int e = 0; e < p.R; e++) { const int d = s.nexts[e]; if (d >= 0) transfer(p, s, e, d, t); }
+        for (int e = 0; e < p.R; e++) {
+          const int d = p.nexts[e];
+          if (d < 0 || (s.meta[e] >> 24) == 0) continue;
+          const uint32_t md = s.meta[d];
+          int dlc = (md >> 8) & 0xff;
+          const int chk = (e < d) ? (md >> 16) & 0xff : md & 0xff;
+          const int dr = transfer(p, s, e, d, chk, dlc);
+          s.meta[d] = (md & 0xffff00ffu) | ((uint32_t)dlc << 8);
+          if (dr) { if (d < p.r) s.ovf[d % p.V] += dr; s.misc[3] += dr; if (s.misc[0] > t) s.misc[0] = t; }
+        }
         s.misc[5] += 1;
       }
       __syncthreads();
-      for (int d = tid; d < p.R; d += blockDim.x) {
-        const uint32_t md = s.meta[d];
-        const int dld = md & 0xff, dlc = (md >> 8) & 0xff;
-        s.tailx[d] = (dlc != dld) ? s.xs[d * CAP + dlc] : INF;
-      }
-    } else {
-      for (int d = tid; d < p.R; d += blockDim.x) {
-        const int u = s.up[d];
-        if (u >= 0) transfer(p, s, u, d, t);
-        const uint32_t md = s.meta[d];
-        const int dld = md & 0xff, dlc = (md >> 8) & 0xff;
-        s.tailx[d] = (dlc != dld) ? s.xs[d * CAP + dlc] : INF;
-      }
+      lc = (s.meta[my_road] >> 8) & 0xff;
+    } else if (is_road && upr >= 0 && (s.meta[upr] >> 24) != 0) {
+      dropped += transfer(p, s, upr, my_road, (upr < my_road) ? ld_pre : ld, lc);
     }
+    if (dropped) {  // OVERFLOW_PENALTY on the road's intersection, traffic_env.py:109-111; done
+      if (is_train) atomicAdd(&s.ovf[dst], dropped);
+      atomicAdd(&s.misc[3], dropped);
+      atomicMin(&s.misc[0], t);
+    }
+    s.tailx[my_road] = (lc != ld) ? xr[lc] : INF;
     __syncthreads();
     if (s.misc[0] <= t) { t++; break; }  // Repeater: `if done: break` (traffic_test.py:55)
   }
@@ -417,15 +398,17 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
   const int last = ticks_run - 1;
 
   // ------------------------------------------------------------ epilogue
-  // vehicle-update / generated-car counters
   for (int o = 16; o > 0; o >>= 1) {
     veh_local += __shfl_xor_sync(FULL, veh_local, o);
     gen_local += __shfl_xor_sync(FULL, gen_local, o);
   }
   if (lane == 0) { atomicAdd(&s.misc[2], veh_local); atomicAdd(&s.misc[4], gen_local); }
+  s.wait[my_road] = wait;
+  __syncthreads();
 
   const int obs_f_len = 2 * p.r + p.I, obs_i_len = 2 * p.r + 2 * p.I;
-  // final light state after `ticks_run` ticks
+  const bool clear_remi = !p.raw && (p.flags & F_REMI);
+  // final light state after `ticks_run` ticks, reward
   for (int i = tid; i < p.I; i += blockDim.x) {
     const bool ls_act = learn_switch && s.act[i];
     const int ph_f = s.phase[i] ^ (ls_act ? (last & 1) : 0);
@@ -433,7 +416,7 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     p.phase[(size_t)env * p.I + i] = (uint8_t)ph_f;
     p.elapsed[(size_t)env * p.I + i] = el_f;
     float rew = (float)(-10 * s.ovf[i]);  // OVERFLOW_PENALTY summed over the ticks: small integers, exact, +0 when none
-    if (!p.raw && (p.flags & F_REMI)) {
+    if (clear_remi) {
       // remi, traffic_env.py:64-78, over the 4 approaches of intersection i in road order
       rew = 0.f;
       const bool pd = s.pdst[i] != 0;
@@ -446,6 +429,7 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
       }
     }
     p.reward[(size_t)env * p.I + i] = rew;
+    p.passed_dst[(size_t)env * p.I + i] = clear_remi ? 0 : s.pdst[i];
     if (p.raw) {
       p.obs_i[(size_t)env * obs_i_len + 2 * p.r + i] = ph_f;
       p.obs_i[(size_t)env * obs_i_len + 2 * p.r + p.I + i] = el_f;
@@ -456,28 +440,19 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     }
     s.ovf[i] = __float_as_int(rew);  // reuse: reward for the return statistic below
   }
-  __syncthreads();  // remi reads wait/pdst of all approaches before they are cleared
-  const bool clear_remi = !p.raw && (p.flags & F_REMI);
-  for (int i = tid; i < p.I; i += blockDim.x)
-    p.passed_dst[(size_t)env * p.I + i] = clear_remi ? 0 : s.pdst[i];
-  for (int e = tid; e < p.r; e += blockDim.x) {
-    const int pd = s.pd[e];
+  if (is_train) {
     if (p.raw) {
-      p.obs_i[(size_t)env * obs_i_len + e] = pd & 0xffff;
-      p.obs_i[(size_t)env * obs_i_len + p.r + e] = pd >> 16;
+      p.obs_i[(size_t)env * obs_i_len + my_road] = passed;
+      p.obs_i[(size_t)env * obs_i_len + p.r + my_road] = det;
     } else {
-      p.obs_f[(size_t)env * obs_f_len + e] = (float)(pd & 0xffff);
-      p.obs_f[(size_t)env * obs_f_len + p.r + e] = (float)(pd >> 16);
+      p.obs_f[(size_t)env * obs_f_len + my_road] = (float)passed;
+      p.obs_f[(size_t)env * obs_f_len + p.r + my_road] = (float)det;
     }
   }
   // pack ring indices back into the row headers, restore the virtual leader's x, flush
-  for (int road = tid; road < p.Rp; road += blockDim.x) {
-    const uint32_t m = s.meta[road];
-    const int ld = m & 0xff, lc = (m >> 8) & 0xff;
-    s.xs[road * CAP + ld] = s.leadx[road];
-    s.xs[road * CAP] = __uint_as_float(pack_meta(ld, lc, (s.pd[road] >> 16) & 0xff));
-    s.vs[road * CAP] = __int_as_float((clear_remi || road >= p.r) ? 0 : s.wait[road]);
-  }
+  xr[ld] = leadx;
+  xr[0] = __uint_as_float(pack_meta(ld, lc, det));
+  vr[0] = __int_as_float((clear_remi || !is_train) ? 0 : wait);
   __syncthreads();
   {
     float4 *gx = reinterpret_cast<float4 *>(p.x + (size_t)env * p.Rp * CAP);
@@ -504,7 +479,6 @@ __global__ void __launch_bounds__(MAX_THREADS) te_step_kernel(const StepParams p
     atomicAdd(&p.stats->ticks, (unsigned long long)ticks_run);
     atomicAdd(&p.stats->vehicle_updates, (unsigned long long)s.misc[2]);
     if (s.misc[3]) atomicAdd(&p.stats->overflows, (unsigned long long)s.misc[3]);
-    // cars generated in ticks that were not run (break on overflow) are not counted
     atomicAdd(&p.stats->cars_generated, (unsigned long long)s.misc[4]);
     if (s.misc[5]) atomicAdd(&p.stats->seq_fallback_ticks, (unsigned long long)s.misc[5]);
   }
