@@ -41,7 +41,9 @@ enum te_flags {
   TE_LEARN_SWITCH = 1 << 0, /* FLAGS.learn_switch, traffic_env.py:225-230 */
   TE_REMI = 1 << 1,         /* te_step returns remi_reward() (traffic_test.py:59-64) instead of the summed env reward */
   TE_AUTO_RESET = 1 << 2,   /* an env that finished (overflow or episode_len) is _reset at the start of its next te_step */
-  TE_VALIDATE = 1 << 3      /* FLAGS.mode == 'validate': record trip times (traffic_env.py:139-157) */
+  TE_VALIDATE = 1 << 3,     /* FLAGS.mode == 'validate': record trip times (traffic_env.py:139-157) */
+  TE_ORDERED_TRANSFERS = 1 << 4 /* verification aid: run every tick's road-to-road transfers in strict road-index order
+                                   (the reference's loop order) instead of in parallel; results are identical */
 };
 
 enum te_arrival_mode {

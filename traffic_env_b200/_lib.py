@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libtraffic_b200.so")
 
 TE_HOST, TE_DEVICE = 0, 1
-TE_LEARN_SWITCH, TE_REMI, TE_AUTO_RESET, TE_VALIDATE = 1, 2, 4, 8
+TE_LEARN_SWITCH, TE_REMI, TE_AUTO_RESET, TE_VALIDATE, TE_ORDERED_TRANSFERS = 1, 2, 4, 8, 16
 TE_ARRIVALS_NONE, TE_ARRIVALS_INJECTED, TE_ARRIVALS_PHILOX = 0, 1, 2
 TE_PARAMS, TE_CAP = 10, 20
 

@@ -40,7 +40,7 @@ constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
 constexpr int WARP_ITEMS = 640;    // per-warp compaction list: 32 roads * 18 cars = 576 entries, padded
 constexpr int MAX_K = 64;
 
-enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8 };
+enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
 enum : int { ARR_NONE = 0, ARR_INJECTED = 1, ARR_PHILOX = 2 };
 
 struct EnvScalars {
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
     s.meta[my_road] = (uint32_t)ld | ((uint32_t)lc << 8) | ((uint32_t)ld_pre << 16) | ((uint32_t)npop << 24);
     __syncthreads();
     // ---------------------------------------------------------------- phase C
-    if (s.misc[1] == t) {
+    if (s.misc[1] == t || (p.flags & F_ORDERED)) {
       if (tid == 0) {
         for (int e = 0; e < p.R; e++) {
           const int d = p.nexts[e];

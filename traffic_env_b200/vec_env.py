@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (TE_ARRIVALS_INJECTED, TE_ARRIVALS_NONE, TE_ARRIVALS_PHILOX, TE_AUTO_RESET, TE_CAP, TE_DEVICE,
-                   TE_HOST, TE_LEARN_SWITCH, TE_REMI, TE_VALIDATE, check)
+                   TE_HOST, TE_LEARN_SWITCH, TE_ORDERED_TRANSFERS, TE_REMI, TE_VALIDATE, check)
 
 ARCHETYPE = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], dtype=np.float32)  # traffic_env.py:35-43
 
@@ -42,13 +42,15 @@ def _ptr(a):
 class VecTrafficEnv(object):
     def __init__(self, m=3, n=3, length=250.0, num_envs=1, rate=0.5, ticks_per_step=10, remi=True,
                  learn_switch=False, auto_reset=False, validate=False, arrivals="philox", local_cars_per_sec=0.12,
-                 entry="all", seed=0, env_id_base=0, device=0, episode_len=0, gamma=0.8, archetype=None):
+                 entry="all", seed=0, env_id_base=0, device=0, episode_len=0, gamma=0.8, archetype=None,
+                 ordered_transfers=False):
         L = _lib.load()
         cfg = _lib.default_config()
         cfg.m, cfg.n, cfg.length, cfg.rate = int(m), int(n), float(length), float(rate)
         cfg.num_envs, cfg.env_id_base, cfg.device = int(num_envs), int(env_id_base), int(device)
         cfg.flags = ((TE_REMI if remi else 0) | (TE_LEARN_SWITCH if learn_switch else 0) |
-                     (TE_AUTO_RESET if auto_reset else 0) | (TE_VALIDATE if validate else 0))
+                     (TE_AUTO_RESET if auto_reset else 0) | (TE_VALIDATE if validate else 0) |
+                     (TE_ORDERED_TRANSFERS if ordered_transfers else 0))
         cfg.entry_spec = entry_spec_of(entry)
         cfg.arrival_mode = {"philox": TE_ARRIVALS_PHILOX, "injected": TE_ARRIVALS_INJECTED,
                             "none": TE_ARRIVALS_NONE}[arrivals]
