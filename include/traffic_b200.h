@@ -109,12 +109,14 @@ int te_get_topology(const te_handle *h, int32_t *dest, int32_t *nexts, int32_t *
 int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *init_phase, int memspace, void *stream);
 
 /* Injected arrival schedule (TE_ARRIVALS_INJECTED).  CSR over (env, tick): the entry roads of
-   env e at schedule tick t are roads[offsets[e*(horizon+1)+t] .. offsets[e*(horizon+1)+t+1]) in
-   arrival order; offsets are absolute into roads.  Replaces the rand_car/rand pair that
-   add_new_cars pulls from (traffic_env.py:274-283).  The schedule cursor of an env advances by
-   one per tick executed and is NOT rewound by reset (the reference never re-seeds).
-   Ticks past the horizon have no arrivals.  Buffers are copied; always host pointers. */
-int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int32_t horizon);
+   env e at arrival-process tick first_tick + t are roads[offsets[e*(horizon+1)+t] ..
+   offsets[e*(horizon+1)+t+1]) in arrival order; offsets are absolute into roads.  Replaces the
+   rand_car/rand pair that add_new_cars pulls from (traffic_env.py:274-283).  The arrival-process
+   tick of an env counts the ticks it has executed since te_create and is NOT rewound by reset (the
+   reference never re-seeds its generator).  Ticks outside [first_tick, first_tick +
+   horizon) have no arrivals; call again with a later window to stream a long schedule.
+   Buffers are copied; always host pointers. */
+int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t first_tick, int32_t horizon);
 
 /* One actor step = Repeater(k_ticks)._step (+ Remi when TE_REMI) for every env, one kernel launch
    (traffic_test.py:37-64).  actions uint8[E, I] (non-zero = 1); obs float[E, 2r+I];

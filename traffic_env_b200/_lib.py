@@ -71,7 +71,7 @@ def load():
     L.te_last_error.restype = C.c_char_p
     L.te_get_topology.argtypes = [vp, vp, vp, vp, vp]
     L.te_reset.argtypes = [vp, vp, vp, C.c_int, vp]
-    L.te_set_arrivals.argtypes = [vp, vp, vp, i32]
+    L.te_set_arrivals.argtypes = [vp, vp, vp, i64, i32]
     L.te_step.argtypes = [vp, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_raw.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.te_remi_reward.argtypes = [vp, vp, C.c_int, vp]

@@ -228,7 +228,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
   p.entry_roads = h->d_entry_roads; p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
-  p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0;
+  p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0; p.sched_first = 0;
 
   // one thread per (padded) road: warp w owns roads [32w, 32w + 32)
   h->warps = h->Rp / GROUP_ROADS;
@@ -303,8 +303,9 @@ extern "C" int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *in
   return 0;
 }
 
-extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int32_t horizon) {
-  if (!h || !offsets || horizon < 0) return fail("te_set_arrivals: bad argument");
+extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t first_tick,
+                               int32_t horizon) {
+  if (!h || !offsets || horizon < 0 || first_tick < 0) return fail("te_set_arrivals: bad argument");
   CU(cudaSetDevice(h->device));
   const size_t E = (size_t)h->cfg.num_envs, no = E * ((size_t)horizon + 1);
   const int64_t total = offsets[no - 1];
@@ -323,6 +324,7 @@ extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16
   CU(cudaMemcpy(h->d_sched_off, offsets, no * sizeof(int64_t), cudaMemcpyHostToDevice));
   if (total > 0) CU(cudaMemcpy(h->d_sched_roads, roads, (size_t)total * sizeof(int16_t), cudaMemcpyHostToDevice));
   h->base.sched_off = h->d_sched_off; h->base.sched_roads = h->d_sched_roads; h->base.horizon = horizon;
+  h->base.sched_first = first_tick;
   return 0;
 }
 

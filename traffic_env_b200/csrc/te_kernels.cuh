@@ -87,6 +87,7 @@ struct StepParams {
   const long long *sched_off;   // [E*(horizon+1)]
   const short *sched_roads;
   int horizon;
+  long long sched_first;        // arrival-process tick of schedule column 0
   const uint32_t *gap_cdf;
   int n_gap;
   uint32_t seed;
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
     if (p.arrival_mode == ARR_INJECTED) {
       const long long cur = es->sched_cursor;
       for (int t = lane; t < p.K; t += 32) {
-        const long long tick = cur + t;
-        if (tick < p.horizon) {
+        const long long tick = cur + t - p.sched_first;
+        if (tick >= 0 && tick < p.horizon) {
           const long long *off = p.sched_off + (size_t)env * (p.horizon + 1) + tick;
           for (long long k = off[0]; k < off[1]; k++) {
             const int idx = p.entry_idx[p.sched_roads[k]];

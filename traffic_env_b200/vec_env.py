@@ -110,8 +110,8 @@ class VecTrafficEnv(object):
             np.asarray(init_phase).astype(bool).reshape(self.num_envs, self.intersections), dtype=np.uint8)
         check(self._L.te_reset(self._h, _ptr(mk), _ptr(ip), TE_HOST, None))
 
-    def set_arrivals(self, schedules):
-        """schedules[e][t] = ordered entry-road ids of env e at schedule tick t."""
+    def set_arrivals(self, schedules, first_tick=0):
+        """schedules[e][t] = ordered entry-road ids of env e at arrival-process tick first_tick + t."""
         E = self.num_envs
         assert len(schedules) == E
         horizon = max(len(s) for s in schedules)
@@ -126,15 +126,15 @@ class VecTrafficEnv(object):
                     base += len(s[t])
                 off[e, t + 1] = base
         roads = np.asarray(roads, dtype=np.int16)
-        self.set_arrivals_csr(off, roads, horizon)
+        self.set_arrivals_csr(off, roads, horizon, first_tick)
 
-    def set_arrivals_csr(self, offsets, roads, horizon):
+    def set_arrivals_csr(self, offsets, roads, horizon, first_tick=0):
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         roads = np.ascontiguousarray(roads, dtype=np.int16)
         assert offsets.size == self.num_envs * (horizon + 1)
         if roads.size == 0:
             roads = np.zeros(1, np.int16)
-        check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(horizon)))
+        check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(first_tick), int(horizon)))
 
     def step(self, actions, k=None):
         """One actor step (Repeater(k) [+ Remi]) for every env; returns (obs, reward, done) host arrays
