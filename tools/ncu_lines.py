@@ -12,6 +12,8 @@ from collections import defaultdict
 
 src_csv, dis_txt = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "te_step_kernel"
+import os
+dis_kern = os.environ.get("DIS_KERNEL", kern)  # mangled-name substring for the disassembly (templates)
 
 # --- nvdisasm: instructions of the kernel in order, with the current //## File "...", line N marker
 lines = open(dis_txt).read().splitlines()
@@ -21,7 +23,7 @@ inline_stack = ""
 dis = []
 for ln in lines:
     if ln.startswith("\t.section\t.text."):
-        in_k = kern in ln
+        in_k = dis_kern in ln
         continue
     if not in_k:
         continue

@@ -65,6 +65,17 @@ struct te_handle {
   int smem_optin;
 };
 
+// One thread per (padded) road.  The register cap follows from the CTA size and the number of CTAs the
+// shared-memory footprint lets an SM hold: 448 threads (10x10 grid) x 2 CTAs -> 72 registers.
+typedef void (*step_kernel_t)(const StepParams);
+static step_kernel_t step_kernel_for(int threads) {
+  if (threads <= 128) return te_step_kernel<128, 4>;
+  if (threads <= 256) return te_step_kernel<256, 3>;
+  if (threads <= 448) return te_step_kernel<448, 2>;
+  if (threads <= 512) return te_step_kernel<512, 1>;
+  return te_step_kernel<1024, 1>;
+}
+
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
 
 extern "C" void te_default_config(te_config *c) {
@@ -223,7 +234,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.idm.rate = cfg->rate; p.idm.x_new = a[0]; p.idm.v_new = a[1]; p.idm.len = a[2]; p.idm.a = a[3];
   p.idm.delta = a[4]; p.idm.v0 = a[5]; p.idm.T = a[7]; p.idm.s0 = a[8];
   { volatile float ab = a[3] * a[6]; p.idm.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
-  p.idm.len_plus = 0.f;
+  p.idm.rcp_two_sqrt_ab = 1.0 / p.idm.two_sqrt_ab;
   p.x = h->x; p.v = h->v; p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
   p.entry_roads = h->d_entry_roads; p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
@@ -236,8 +247,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry);
   if (L.total > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", L.total, h->smem_optin); }
-  CUH(cudaFuncSetAttribute(te_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-  CUH(cudaFuncSetAttribute(te_step_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUH(cudaFuncSetAttribute(step_kernel_for(h->Rp), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
   te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
@@ -351,8 +361,7 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
   }
   const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry);
   CU(cudaEventRecord(h->ev0, st));
-  if (h->Rp <= 512) te_step_kernel<512><<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
-  else te_step_kernel<1024><<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
+  step_kernel_for(h->Rp)<<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
@@ -562,7 +571,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   IdmConst c;
   c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
   { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
-  c.len_plus = 0.f;
+  c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));

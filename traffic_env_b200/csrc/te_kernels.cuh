@@ -6,8 +6,9 @@
 // as two float planes x[Rp][20], v[Rp][20] - every car has the same archetype
 // (traffic_env.py:35-43), so x and v are the only dynamic fields - and flushed once.
 //
-// Roads map to warps: warp w owns roads [32w, 32w+32), lane = road, for the whole launch; the
-// road's ring indices and counters live in that lane's registers.
+// Roads map to warps: lane l of warp w owns road l * nwarps + w for the whole launch (interleaved, so
+// every warp gets the same mix of entry, interior and exit roads and the two CTA barriers of a tick
+// wait on balanced warps); the road's ring indices and counters live in that lane's registers.
 //
 // Per tick (order of traffic_env.py:224-248, see DESIGN.md "tick phases"):
 //   phase A  (warp-local, no CTA barrier inside)
@@ -182,8 +183,8 @@ __device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int 
   return dropped;
 }
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry);
   const Smem s = carve(smem_raw, L);
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
   __syncthreads();
 
   // ---- lane = road: ring indices, counters and topology of my road live in registers
-  const int my_road = tid;                       // blockDim.x == Rp
+  const int nwarps = blockDim.x >> 5;            // blockDim.x == Rp
+  const int my_road = lane * nwarps + warp;
   const bool is_road = my_road < p.R, is_train = my_road < p.r;
   float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
   int ld, lc, wait, det, passed = 0;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(MAXT) te_step_kernel(const StepParams p) {
       if (valid) {
         const int tt = ldj + k;
         const int slot = tt < RING ? tt + 1 : tt - (RING - 1);   // ((ld + k) mod 19) + 1
-        const int rbase = (warp * GROUP_ROADS + j) * CAP;
+        const int rbase = (j * nwarps + warp) * CAP;
         o = rbase + slot;
         float x = s.xs[o], v = s.vs[o];
         float xl = lxj, vl = 0.f, ll = 0.f;                  // virtual leader: v = 0, l = 0
