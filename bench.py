@@ -242,12 +242,12 @@ def b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # under load from the warm-up on: the timed region alone can be shorter than one sample
     for s in range(a.warmup):
         device_step(s)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     st0 = env.stats()
     launches[0] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
