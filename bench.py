@@ -347,6 +347,10 @@ def b200_arm(a):
                "sample": "1 env of %s on 1 core (oracle/traffic_oracle.c): 60-actor-step pre-roll, then %.0f s of "
                "actor steps (%d steps)" % (a.workload, r1["seconds"], r1["actor_steps"])}
 
+    arith_peak = None
+    if rank == 0:
+        from traffic_env_b200.vec_env import idm_arithmetic_peak
+        arith_peak = idm_arithmetic_peak(device=local)
     if rank == 0:
         sec = ms_max * 1e-3
         value = vu_all / sec
@@ -365,6 +369,9 @@ def b200_arm(a):
                          "algorithmic_bytes_per_env_step": bytes_env, "cars_per_env": cars_env,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "the fused K-tick kernel is issue/FP64-pipe bound, not HBM bound (SURVEY.md 8d); see roofline_issue"},
+            "roofline_compute": {"bound": "idm arithmetic (registers only, all lanes busy: te_idm_peak micro-kernel)",
+                                 "achieved": float(np.mean(kvu)) / (k_ms * 1e-3), "peak": arith_peak,
+                                 "unit": "vehicle-updates/s", "frac": float(np.mean(kvu)) / (k_ms * 1e-3) / arith_peak},
             "roofline_issue": {"ops_per_vehicle_update": OPS_PER_UPDATE,
                                "achieved_gops": float(np.mean(kvu)) * OPS_PER_UPDATE / (k_ms * 1e-3) / 1e9,
                                "fp32_peak_gops_nominal_at_clock": fp32_peak / 1e9 if fp32_peak else None},

@@ -152,14 +152,21 @@ int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *
 /* Counters since te_create (device -> host; synchronises the device). */
 int te_get_stats(te_handle *h, te_stats *out);
 
-/* Trip times recorded in validate mode (traffic_env.py:154), seconds; returns the number available
-   through *count and copies up to cap of them.  Clears the buffer when `clear` is non-zero. */
-int te_get_trip_times(te_handle *h, float *out, int64_t cap, int64_t *count, int clear);
+/* Trip times recorded in validate mode (advance_hack, traffic_env.py:139-157): seconds between a car's
+   arrival and its leaving the map, one (env, trip) pair per car, sorted by env and, within an env, in the
+   order the reference appends them (tick, road index, pop order).  *count receives the number available;
+   up to cap pairs are copied (either output may be NULL).  `clear` empties the device buffer afterwards. */
+int te_get_trip_times(te_handle *h, int32_t *env_out, float *trip_out, int64_t cap, int64_t *count, int clear);
 
 int te_synchronize(te_handle *h);
 
 /* Kernel time of the last te_step/te_step_raw launch in milliseconds (CUDA events on the launch stream). */
 int te_last_kernel_ms(te_handle *h, float *ms);
+
+/* Arithmetic-only ceiling of the path: vehicle-updates/s of a micro-kernel in which every lane of a fully
+   occupied GPU does nothing but dependent IDM updates (traffic_env.py:50-62) in registers.  Used by bench.py
+   as the compute roofline of the step kernel. */
+int te_idm_peak(int device, const float *archetype, float rate, int32_t iters, double *updates_per_sec);
 
 /* ---- test hooks (host pointers): device arithmetic exposed for bit-exactness tests */
 /* out[i] = device restatement of glibc powf(x[i], y) (numba lowers float32 ** to libm powf). */

@@ -103,3 +103,44 @@ def test_raw_and_fused_agree():
     sa, sb = a.get_state(), b.get_state()
     for k in ("leading", "lastcar", "waiting", "passed_dst"):
         assert (sa[k] == sb[k]).all(), k
+
+
+def test_validate_mode_trip_times():
+    """TE_VALIDATE: per-car birth ticks travel with the cars; trip times of cars leaving the map equal the
+    reference's advance_hack list (traffic_env.py:139-157), values and order."""
+    g = np.load(os.path.join(GOLDEN, "validate_3x3.npz"))
+    env = make_env(g, remi=False, validate=True)
+    sched = unpack_schedule(g["sched_off"], g["sched_roads"])
+    env.set_arrivals([sched])
+    env.reset(init_phase=g["init_phase"][None])
+    got = []
+    for t in range(int(g["ticks"])):
+        obs, rew, done = env.step_raw(g["actions"][t][None])
+        if t % 97 == 0:
+            got.extend(env.trip_times(clear=True)[1])
+    envs, trips = env.trip_times(clear=True)
+    got.extend(trips)
+    want = g["trip_times"]
+    assert len(want) > 50
+    assert np.asarray(got, np.float64).tobytes() == want.tobytes()
+    st = env.get_state(0, 1)
+    assert (st["leading"][0] == g["ck600_leading"]).all()
+
+
+def test_validate_mode_fused_steps_same_trips():
+    """The fused K-tick launch records the same trips as K raw ticks."""
+    g = np.load(os.path.join(GOLDEN, "validate_3x3.npz"))
+    sched = unpack_schedule(g["sched_off"], g["sched_roads"])
+    a = make_env(g, remi=False, validate=True)
+    b = make_env(g, remi=False, validate=True, ticks_per_step=10)
+    for env in (a, b):
+        env.set_arrivals([sched])
+        env.reset(init_phase=g["init_phase"][None])
+    for s in range(40):
+        act = g["actions"][10 * s][None]
+        for _ in range(10):
+            a.step_raw(act)
+        _, _, done = b.step(act)
+        assert not done[0]
+    ta, tb = a.trip_times()[1], b.trip_times()[1]
+    assert len(ta) > 20 and ta.tobytes() == tb.tobytes()

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -60,7 +61,7 @@ struct te_handle {
   uint8_t *d_actions, *d_done, *d_mask, *d_init_phase;
   float *d_obs_f, *d_reward;
   int *d_obs_i, *d_cars;
-  float *d_trips; unsigned long long *d_trip_count; long long trip_cap;
+  float *w; TripRecord *d_trips; unsigned long long *d_trip_count; long long trip_cap;
   int warps;
   int smem_optin;
 };
@@ -68,12 +69,17 @@ struct te_handle {
 // One thread per (padded) road.  The register cap follows from the CTA size and the number of CTAs the
 // shared-memory footprint lets an SM hold: 448 threads (10x10 grid) x 2 CTAs -> 72 registers.
 typedef void (*step_kernel_t)(const StepParams);
-static step_kernel_t step_kernel_for(int threads) {
-  if (threads <= 128) return te_step_kernel<128, 4>;
-  if (threads <= 256) return te_step_kernel<256, 3>;
-  if (threads <= 448) return te_step_kernel<448, 2>;
-  if (threads <= 512) return te_step_kernel<512, 1>;
-  return te_step_kernel<1024, 1>;
+static step_kernel_t step_kernel_for(int threads, bool validate) {
+  if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
+    if (threads <= 256) return te_step_kernel<256, 2, true>;
+    if (threads <= 512) return te_step_kernel<512, 1, true>;
+    return te_step_kernel<1024, 1, true>;
+  }
+  if (threads <= 128) return te_step_kernel<128, 4, false>;
+  if (threads <= 256) return te_step_kernel<256, 3, false>;
+  if (threads <= 448) return te_step_kernel<448, 2, false>;
+  if (threads <= 512) return te_step_kernel<512, 1, false>;
+  return te_step_kernel<1024, 1, false>;
 }
 
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
@@ -122,7 +128,7 @@ static std::vector<uint32_t> build_gap_cdf(double cars_per_tick) {
 static void free_handle(te_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  void *ptrs[] = {h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
+  void *ptrs[] = {h->w, h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
                   h->d_entry_roads, h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
                   h->d_done, h->d_mask, h->d_init_phase, h->d_reward, h->d_obs_i /* d_obs_f aliases it */, h->d_cars,
                   h->d_trips, h->d_trip_count};
@@ -150,7 +156,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   te_handle *h = new te_handle();
   memset((void *)&h->base, 0, sizeof(h->base));
   h->cfg = *cfg; h->device = cfg->device;
-  h->x = h->v = nullptr; h->elapsed = nullptr; h->phase = h->passed_dst = nullptr; h->env = nullptr; h->stats = nullptr;
+  h->x = h->v = h->w = nullptr; h->elapsed = nullptr; h->phase = h->passed_dst = nullptr; h->env = nullptr; h->stats = nullptr;
   h->d_nexts = h->d_up = h->d_entry_roads = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
   h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
   h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
@@ -190,6 +196,13 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
   CUH(dalloc(&h->x, E * h->Rp * CAP)); CUH(dalloc(&h->v, E * h->Rp * CAP));
+  if (cfg->flags & TE_VALIDATE) {
+    CUH(dalloc(&h->w, E * h->Rp * CAP));
+    CUH(cudaMemset(h->w, 0, E * h->Rp * CAP * sizeof(float)));
+    h->trip_cap = 1 << 20;
+    CUH(dalloc(&h->d_trips, (size_t)h->trip_cap)); CUH(dalloc(&h->d_trip_count, 1));
+    CUH(cudaMemset(h->d_trip_count, 0, sizeof(unsigned long long)));
+  }
   CUH(dalloc(&h->elapsed, E * h->I)); CUH(dalloc(&h->phase, E * h->I)); CUH(dalloc(&h->passed_dst, E * h->I));
   CUH(dalloc(&h->env, E)); CUH(dalloc(&h->stats, 1));
   CUH(dalloc(&h->d_nexts, (size_t)h->Rp)); CUH(dalloc(&h->d_up, (size_t)h->Rp));
@@ -235,7 +248,8 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.idm.delta = a[4]; p.idm.v0 = a[5]; p.idm.T = a[7]; p.idm.s0 = a[8];
   { volatile float ab = a[3] * a[6]; p.idm.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
   p.idm.rcp_two_sqrt_ab = 1.0 / p.idm.two_sqrt_ab;
-  p.x = h->x; p.v = h->v; p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
+  p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
+  p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
   p.entry_roads = h->d_entry_roads; p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
@@ -245,9 +259,10 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->warps = h->Rp / GROUP_ROADS;
   if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
   CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry);
+  const bool validate = (cfg->flags & TE_VALIDATE) != 0;
+  const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry, validate);
   if (L.total > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", L.total, h->smem_optin); }
-  CUH(cudaFuncSetAttribute(step_kernel_for(h->Rp), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  CUH(cudaFuncSetAttribute(step_kernel_for(h->Rp, validate), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
   te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
@@ -359,9 +374,10 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, nullptr, nullptr, 1);
     CU(cudaGetLastError());
   }
-  const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry);
+  const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
+  const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry, validate);
   CU(cudaEventRecord(h->ev0, st));
-  step_kernel_for(h->Rp)<<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
+  step_kernel_for(h->Rp, validate)<<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
@@ -530,11 +546,26 @@ extern "C" int te_get_stats(te_handle *h, te_stats *out) {
   return 0;
 }
 
-extern "C" int te_get_trip_times(te_handle *h, float *out, int64_t cap, int64_t *count, int clear) {
-  (void)out; (void)cap; (void)clear;
+extern "C" int te_get_trip_times(te_handle *h, int32_t *env_out, float *trip_out, int64_t cap, int64_t *count, int clear) {
   if (!h || !count) return fail("te_get_trip_times: null argument");
   if (!(h->cfg.flags & TE_VALIDATE)) return fail("te_get_trip_times: handle was not created with TE_VALIDATE");
-  return fail("te_get_trip_times: validate mode is not implemented yet");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long n = 0;
+  CU(cudaMemcpy(&n, h->d_trip_count, sizeof(n), cudaMemcpyDeviceToHost));
+  if ((long long)n > h->trip_cap) return fail("te_get_trip_times: %llu trips recorded but the buffer holds %lld; read more often", n, h->trip_cap);
+  *count = (int64_t)n;
+  if (n && (env_out || trip_out)) {
+    std::vector<TripRecord> recs(n);
+    CU(cudaMemcpy(recs.data(), h->d_trips, n * sizeof(TripRecord), cudaMemcpyDeviceToHost));
+    // the reference appends in (env-local) tick order, road-index order, pop order
+    std::sort(recs.begin(), recs.end(), [](const TripRecord &a, const TripRecord &b) {
+      return a.env != b.env ? a.env < b.env : a.order < b.order; });
+    const int64_t m = (int64_t)n < cap ? (int64_t)n : cap;
+    for (int64_t i = 0; i < m; i++) { if (env_out) env_out[i] = recs[i].env; if (trip_out) trip_out[i] = recs[i].trip; }
+  }
+  if (clear) CU(cudaMemset(h->d_trip_count, 0, sizeof(unsigned long long)));
+  return 0;
 }
 
 extern "C" int te_synchronize(te_handle *h) {
@@ -581,6 +612,33 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   CU(cudaMemcpy(x_out, d[5], n * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(v_out, d[6], n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 7; i++) cudaFree(d[i]);
+  return 0;
+}
+
+extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters, double *updates_per_sec) {
+  if (!a || !updates_per_sec || iters < 1) return fail("te_idm_peak: bad argument");
+  CU(cudaSetDevice(device));
+  IdmConst c;
+  c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
+  { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
+  c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
+  float *sink = nullptr;
+  CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  te_idm_peak_kernel<<<blocks, threads>>>(c, iters / 4 + 1, sink);  // warm-up
+  CU(cudaEventRecord(e0));
+  te_idm_peak_kernel<<<blocks, threads>>>(c, iters, sink);
+  CU(cudaEventRecord(e1));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  *updates_per_sec = (double)threads * blocks * iters / (ms * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
   return 0;
 }
 

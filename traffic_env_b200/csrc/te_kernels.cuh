@@ -60,6 +60,14 @@ struct DeviceStats {
   double return_sum, disc_return_sum;
 };
 
+// One car that left the map in validate mode (advance_hack, traffic_env.py:153-154).  `order` restores the
+// reference's list order (tick, then road index, then pop order) after a host-side sort.
+struct TripRecord {
+  int env;
+  float trip;             // (tick - w) / 2, seconds
+  unsigned long long order;
+};
+
 struct StepParams {
   int V, r, R, Rp, I, n_entry, G;
   int num_envs;
@@ -70,6 +78,10 @@ struct StepParams {
   IdmConst idm;
   // state (HBM)
   float *x, *v;           // [E][Rp][20]; slot 0 of a row carries packed ring indices (see pack_meta)
+  float *w;               // [E][Rp][20] birth tick of each car (validate mode only, traffic_env.py:34,279)
+  TripRecord *trips;      // validate mode: append buffer of finished trips
+  unsigned long long *trip_count;
+  long long trip_cap;
   int *elapsed;           // [E][I]
   uint8_t *phase, *passed_dst;  // [E][I]
   EnvScalars *env;
@@ -101,16 +113,17 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 }
 
 struct SmemLayout {
-  int xs, vs, tabs, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
+  int xs, vs, ws, tabs, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
 };
 
 __host__ __device__ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
 
-__host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_entry) {
+__host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_entry, bool validate) {
   SmemLayout L;
   int o = 0;
   L.xs = o; o += Rp * CAP * 4;
   L.vs = o; o += Rp * CAP * 4;
+  L.ws = o; o += validate ? Rp * CAP * 4 : 0;
   L.tabs = o; o += (int)sizeof(PowfTables);            // 512 B, 8-aligned
   L.tailx = o; o += Rp * 4;
   L.meta = o; o += Rp * 4;
@@ -133,20 +146,21 @@ __device__ __forceinline__ int ring_count(int ld, int lc) { return lc - ld + (ld
 
 // add_car (traffic_env.py:97-114) for one identical-archetype car at (xin, vin); `chk` is the value
 // of leading[road] the reference would see at that moment.  Returns false when the ring is full.
-__device__ __forceinline__ bool ring_push(float *xr, float *vr, int chk, int &lc, float xin, float vin,
-                                          const IdmConst &c) {
+__device__ __forceinline__ bool ring_push(float *xr, float *vr, float *wr, int chk, int &lc, float xin, float vin,
+                                          float win, const IdmConst &c) {
   const int pos = ring_wrap(lc + 1);
   float start = __int_as_float(0x7f800000);
   if (lc != chk) start = __fsub_rn(__fsub_rn(xr[lc], c.len), c.s0);
   if (pos == chk) return false;
   xr[pos] = (start < xin) ? start : xin;
   vr[pos] = vin;
+  if (wr) wr[pos] = win;  // validate mode only
   lc = pos;
   return true;
 }
 
 struct Smem {
-  float *xs, *vs, *tailx;
+  float *xs, *vs, *ws, *tailx;
   uint32_t *meta;        // published after phase A: leading | lastcar << 8 | pre-pop leading << 16 | npop << 24
   int *wait, *elapsed, *ovf;
   uint32_t *snap;
@@ -157,7 +171,8 @@ struct Smem {
 
 __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) {
   Smem s;
-  s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs); s.tailx = (float *)(base + L.tailx);
+  s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs); s.ws = (float *)(base + L.ws);
+  s.tailx = (float *)(base + L.tailx);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
   s.misc = (int *)(base + L.misc); s.items = base + L.items; s.phase = base + L.phase; s.act = base + L.act;
@@ -169,24 +184,26 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) 
 // traffic_env.py:126-132).  `chk` is the value of leading[d] the reference sees at that moment:
 // the pre-pop value when u < d (the reference inserts before d's own pops of this tick).
 // Returns the number of cars dropped on a full ring.
-__device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int u, int d, int chk, int &dlc) {
+__device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int u, int d, int chk, int &dlc,
+                                        bool validate) {
   const uint32_t mu = s.meta[u];
   const int np = mu >> 24;
   int slot = (mu >> 16) & 0xff, dropped = 0;
-  float *xd = s.xs + d * CAP, *vd = s.vs + d * CAP;
+  float *xd = s.xs + d * CAP, *vd = s.vs + d * CAP, *wd = validate ? s.ws + d * CAP : nullptr;
   for (int k = 0; k < np; k++) {
     slot = ring_wrap(slot + 1);
     const float xin = __fsub_rn(s.xs[u * CAP + slot], p.length);
     const float vin = s.vs[u * CAP + slot];
-    if (!ring_push(xd, vd, chk, dlc, xin, vin, p.idm)) dropped++;
+    const float win = validate ? s.ws[u * CAP + slot] : 0.f;
+    if (!ring_push(xd, vd, wd, chk, dlc, xin, vin, win, p.idm)) dropped++;
   }
   return dropped;
 }
 
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, bool VALIDATE>
 __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry);
+  const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry, VALIDATE);
   const Smem s = carve(smem_raw, L);
   const int env = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -202,6 +219,11 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     float4 *sx = reinterpret_cast<float4 *>(s.xs), *sv = reinterpret_cast<float4 *>(s.vs);
     const int n4 = p.Rp * (CAP / 4);
     for (int i = tid; i < n4; i += blockDim.x) { sx[i] = gx[i]; sv[i] = gv[i]; }
+    if (VALIDATE) {
+      const float4 *gw = reinterpret_cast<const float4 *>(p.w + (size_t)env * p.Rp * CAP);
+      float4 *sw = reinterpret_cast<float4 *>(s.ws);
+      for (int i = tid; i < n4; i += blockDim.x) sw[i] = gw[i];
+    }
   }
   for (int i = tid; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long *>(s.tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
@@ -261,6 +283,8 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   const int my_road = lane * nwarps + warp;
   const bool is_road = my_road < p.R, is_train = my_road < p.r;
   float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
+  float *wr = VALIDATE ? s.ws + my_road * CAP : nullptr;
+  const float steps0 = es->steps;  // np.float32 tick counter at the start of this launch (small integer: exact)
   int ld, lc, wait, det, passed = 0;
   float leadx;
   {
@@ -286,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       const int na = s.cnt[t * p.n_entry + ei];
       for (int k = 0; k < na; k++) {
         gen_local++;
-        if (!ring_push(xr, vr, ld, lc, c.x_new, c.v_new, c)) dropped++;
+        if (!ring_push(xr, vr, wr, ld, lc, c.x_new, c.v_new, steps0 + (float)t, c)) dropped++;  // car[wi] = tick, :279
       }
     }
     if (is_train) {  // update_lights, traffic_env.py:81-94
@@ -355,6 +379,21 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         f = f2; npop++;
       }
       if (npop > 0) {
+        if (VALIDATE && nxt < 0 && is_road) {
+          // advance_hack, traffic_env.py:153-154: trip time of every car that leaves the map
+          const unsigned long long base = atomicAdd(p.trip_count, (unsigned long long)npop);
+          int fs = ld;
+          for (int k = 0; k < npop; k++) {
+            fs = ring_wrap(fs + 1);
+            if ((long long)(base + k) < p.trip_cap) {
+              TripRecord rec;
+              rec.env = env;
+              rec.trip = __fsub_rn(steps0 + (float)t, wr[fs]) / 2.0f;
+              rec.order = (((unsigned long long)(es->sched_cursor + t)) << 24) | ((unsigned long long)my_road << 8) | (unsigned)k;
+              p.trips[base + k] = rec;
+            }
+          }
+        }
         ld = f;
         if (nxt >= 0) {
           passed += npop;                               // traffic_env.py:127
@@ -377,7 +416,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           const uint32_t md = s.meta[d];
           int dlc = (md >> 8) & 0xff;
           const int chk = (e < d) ? (md >> 16) & 0xff : md & 0xff;
-          const int dr = transfer(p, s, e, d, chk, dlc);
+          const int dr = transfer(p, s, e, d, chk, dlc, VALIDATE);
           s.meta[d] = (md & 0xffff00ffu) | ((uint32_t)dlc << 8);
           if (dr) { if (d < p.r) s.ovf[d % p.V] += dr; s.misc[3] += dr; if (s.misc[0] > t) s.misc[0] = t; }
         }
@@ -386,7 +425,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       __syncthreads();
       lc = (s.meta[my_road] >> 8) & 0xff;
     } else if (is_road && upr >= 0 && (s.meta[upr] >> 24) != 0) {
-      dropped += transfer(p, s, upr, my_road, (upr < my_road) ? ld_pre : ld, lc);
+      dropped += transfer(p, s, upr, my_road, (upr < my_road) ? ld_pre : ld, lc, VALIDATE);
     }
     if (dropped) {  // OVERFLOW_PENALTY on the road's intersection, traffic_env.py:109-111; done
       if (is_train) atomicAdd(&s.ovf[dst], dropped);
@@ -463,6 +502,11 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     const float4 *sx = reinterpret_cast<const float4 *>(s.xs), *sv = reinterpret_cast<const float4 *>(s.vs);
     const int n4 = p.Rp * (CAP / 4);
     for (int i = tid; i < n4; i += blockDim.x) { gx[i] = sx[i]; gv[i] = sv[i]; }
+    if (VALIDATE) {
+      float4 *gw = reinterpret_cast<float4 *>(p.w + (size_t)env * p.Rp * CAP);
+      const float4 *sw = reinterpret_cast<const float4 *>(s.ws);
+      for (int i = tid; i < n4; i += blockDim.x) gw[i] = sw[i];
+    }
   }
   if (tid == 0) {
     const bool overflowed = s.misc[0] != 0x7fffffff;
@@ -587,6 +631,24 @@ __global__ void te_test_idm_kernel(IdmConst c, const float *xl, const float *vl,
     xo[i] = xx; vo[i] = vv;
   }
 }
+// Arithmetic-only ceiling: every lane runs `iters` dependent IDM updates of one car behind a leader that
+// drives at constant speed (registers only, full-precision path: both divisions and powf every time).
+__global__ void te_idm_peak_kernel(IdmConst c, int iters, float *sink) {
+  __shared__ PowfTables tabs;
+  for (int i = threadIdx.x; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
+    reinterpret_cast<unsigned long long *>(&tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
+  __syncthreads();
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  float x = 0.f, v = 5.f + 0.001f * (float)(gid & 1023);
+  float xl = 30.f + 0.01f * (float)(gid & 255);
+  const float vl = 9.f, step = __fmul_rn(vl, c.rate);
+  for (int i = 0; i < iters; i++) {
+    idm_update(c, &tabs, xl, vl, c.len, x, v);
+    xl = __fadd_rn(xl, step);
+  }
+  sink[gid] = x + v;
+}
+
 __global__ void te_test_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
   uint32_t o[4];
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);

@@ -120,6 +120,7 @@ class TrafficEnv(gym.Env):
             self._key = self._sim_key()
             self._sim = VecTrafficEnv(m=g.m, n=g.n, length=float(g.len), num_envs=1, rate=float(FLAGS.rate),
                                       remi=False, learn_switch=bool(FLAGS.learn_switch), arrivals="injected",
+                                      validate=(_mode() == 'validate'),
                                       entry=self._spec, device=int(os.environ.get("TRAFFIC_B200_DEVICE", "0")))
             assert (self._sim.nexts == g.nexts).all() and (self._sim.entrypoints == g.entrypoints).all()
             self._sched_begin = self._sched_end = self._ticks_total = 0
@@ -146,6 +147,8 @@ class TrafficEnv(gym.Env):
         self._sim.set_arrivals([self._window], first_tick=self._sched_begin)
 
     def _pull(self, obs_raw, rewards, ticks):
+        if self._key[-1]:  # validate mode: trip times of the cars that left the map (traffic_env.py:154)
+            self.trip_times.extend(np.float32(t) for t in self._sim.trip_times(clear=True)[1])
         self.obs[:] = obs_raw
         self._mirror[:] = obs_raw
         self.rewards[:] = rewards

@@ -205,6 +205,15 @@ class VecTrafficEnv(object):
                  ("obs", np.int32), ("waiting", np.int32), ("passed_dst", np.uint8), ("steps", np.float32))]
         check(self._L.te_set_state(self._h, env_begin, count, *[a.ctypes.data for a in arrs]))
 
+    def trip_times(self, clear=True):
+        """Validate mode: (env ids, trip times in seconds) of the cars that left the map since the last clear."""
+        n = C.c_int64()
+        check(self._L.te_get_trip_times(self._h, None, None, 0, C.byref(n), 0))
+        envs = np.empty(n.value, np.int32)
+        trips = np.empty(n.value, np.float32)
+        check(self._L.te_get_trip_times(self._h, envs.ctypes.data, trips.ctypes.data, n.value, C.byref(n), int(clear)))
+        return envs, trips
+
     def stats(self):
         s = _lib.TeStats()
         check(self._L.te_get_stats(self._h, C.byref(s)))
@@ -217,3 +226,12 @@ class VecTrafficEnv(object):
 
     def synchronize(self):
         check(self._L.te_synchronize(self._h))
+
+
+def idm_arithmetic_peak(device=0, rate=0.5, archetype=None, iters=4000):
+    """vehicle-updates/s of the IDM arithmetic alone on a fully occupied GPU (te_idm_peak)."""
+    L = _lib.load()
+    arch = np.ascontiguousarray(ARCHETYPE if archetype is None else archetype, dtype=np.float32)
+    out = C.c_double()
+    check(L.te_idm_peak(int(device), arch.ctypes.data, float(rate), int(iters), C.byref(out)))
+    return out.value
