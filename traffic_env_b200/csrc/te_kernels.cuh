@@ -113,7 +113,7 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 }
 
 struct SmemLayout {
-  int xs, vs, ws, tabs, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
+  int xs, vs, ws, tabs, mbar, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
 };
 
 __host__ __device__ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -125,6 +125,7 @@ __host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_en
   L.vs = o; o += Rp * CAP * 4;
   L.ws = o; o += validate ? Rp * CAP * 4 : 0;
   L.tabs = o; o += (int)sizeof(PowfTables);            // 512 B, 8-aligned
+  L.mbar = o; o += 8;
   L.tailx = o; o += Rp * 4;
   L.meta = o; o += Rp * 4;
   L.wait = o; o += Rp * 4;
@@ -139,6 +140,36 @@ __host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_en
   L.cnt = o; o += align_up(K * (n_entry > 0 ? n_entry : 1), 16);
   L.total = align_up(o, 16);
   return L;
+}
+
+// ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier: the env's ring planes are contiguous in HBM, so
+// one elected thread moves each plane with a single instruction while the other threads set up the tick loop.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "TE_WAIT_%=:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@!p bra TE_WAIT_%=;\n"
+               "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ int ring_wrap(int a) { return a >= CAP ? 1 : a; }
@@ -163,6 +194,7 @@ struct Smem {
   float *xs, *vs, *ws, *tailx;
   uint32_t *meta;        // published after phase A: leading | lastcar << 8 | pre-pop leading << 16 | npop << 24
   int *wait, *elapsed, *ovf;
+  unsigned long long *mbar;
   uint32_t *snap;
   int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks
   uint8_t *items, *phase, *act, *pdst, *cnt;
@@ -172,7 +204,7 @@ struct Smem {
 __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) {
   Smem s;
   s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs); s.ws = (float *)(base + L.ws);
-  s.tailx = (float *)(base + L.tailx);
+  s.tailx = (float *)(base + L.tailx); s.mbar = (unsigned long long *)(base + L.mbar);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
   s.misc = (int *)(base + L.misc); s.items = base + L.items; s.phase = base + L.phase; s.act = base + L.act;
@@ -213,17 +245,14 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   EnvScalars *es = p.env + env;
 
   // ------------------------------------------------------------ prologue: stage the env
-  {
-    const float4 *gx = reinterpret_cast<const float4 *>(p.x + (size_t)env * p.Rp * CAP);
-    const float4 *gv = reinterpret_cast<const float4 *>(p.v + (size_t)env * p.Rp * CAP);
-    float4 *sx = reinterpret_cast<float4 *>(s.xs), *sv = reinterpret_cast<float4 *>(s.vs);
-    const int n4 = p.Rp * (CAP / 4);
-    for (int i = tid; i < n4; i += blockDim.x) { sx[i] = gx[i]; sv[i] = gv[i]; }
-    if (VALIDATE) {
-      const float4 *gw = reinterpret_cast<const float4 *>(p.w + (size_t)env * p.Rp * CAP);
-      float4 *sw = reinterpret_cast<float4 *>(s.ws);
-      for (int i = tid; i < n4; i += blockDim.x) sw[i] = gw[i];
-    }
+  const uint32_t plane_bytes = (uint32_t)p.Rp * CAP * 4;  // multiple of 16: Rp is a multiple of 32 roads of 80 B
+  if (tid == 0) {
+    mbar_init(s.mbar, 1);
+    fence_proxy_async();
+    mbar_expect_tx(s.mbar, plane_bytes * (VALIDATE ? 3u : 2u));
+    bulk_load(s.xs, p.x + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+    bulk_load(s.vs, p.v + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+    if (VALIDATE) bulk_load(s.ws, p.w + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
   }
   for (int i = tid; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long *>(s.tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
@@ -277,6 +306,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     }
   }
   __syncthreads();
+  mbar_wait(s.mbar, 0);  // the ring planes have landed
 
   // ---- lane = road: ring indices, counters and topology of my road live in registers
   const int nwarps = blockDim.x >> 5;            // blockDim.x == Rp
@@ -495,18 +525,12 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   xr[ld] = leadx;
   xr[0] = __uint_as_float(pack_meta(ld, lc, det));
   vr[0] = __int_as_float((clear_remi || !is_train) ? 0 : wait);
+  fence_proxy_async();  // my generic-proxy writes to the planes become visible to the bulk-copy engine
   __syncthreads();
-  {
-    float4 *gx = reinterpret_cast<float4 *>(p.x + (size_t)env * p.Rp * CAP);
-    float4 *gv = reinterpret_cast<float4 *>(p.v + (size_t)env * p.Rp * CAP);
-    const float4 *sx = reinterpret_cast<const float4 *>(s.xs), *sv = reinterpret_cast<const float4 *>(s.vs);
-    const int n4 = p.Rp * (CAP / 4);
-    for (int i = tid; i < n4; i += blockDim.x) { gx[i] = sx[i]; gv[i] = sv[i]; }
-    if (VALIDATE) {
-      float4 *gw = reinterpret_cast<float4 *>(p.w + (size_t)env * p.Rp * CAP);
-      const float4 *sw = reinterpret_cast<const float4 *>(s.ws);
-      for (int i = tid; i < n4; i += blockDim.x) gw[i] = sw[i];
-    }
+  if (tid == 0) {
+    bulk_store(p.x + (size_t)env * p.Rp * CAP, s.xs, plane_bytes);
+    bulk_store(p.v + (size_t)env * p.Rp * CAP, s.vs, plane_bytes);
+    if (VALIDATE) bulk_store(p.w + (size_t)env * p.Rp * CAP, s.ws, plane_bytes);
   }
   if (tid == 0) {
     const bool overflowed = s.misc[0] != 0x7fffffff;
@@ -528,6 +552,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (s.misc[3]) atomicAdd(&p.stats->overflows, (unsigned long long)s.misc[3]);
     atomicAdd(&p.stats->cars_generated, (unsigned long long)s.misc[4]);
     if (s.misc[5]) atomicAdd(&p.stats->seq_fallback_ticks, (unsigned long long)s.misc[5]);
+    bulk_commit_wait();  // the flush has left shared memory and reached HBM before the CTA retires
   }
 }
 
