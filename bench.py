@@ -305,18 +305,16 @@ def b200_arm(a):
     # end to end through the public API with HOST buffers: what the greedy agent does (greedy.py:13-17)
     e2e = None
     if not a.no_e2e:
-        h_act = torch.zeros((E, I), dtype=torch.uint8).pin_memory()
-        h_obs = torch.empty((E, OL), dtype=torch.float32).pin_memory()
-        h_rew = torch.empty((E, I), dtype=torch.float32).pin_memory()
-        h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
-        h_cars = np.empty((E, R), np.int32)
+        h_act = np.zeros((E, I), dtype=np.uint8)
         wts = np.array([1, 1, -1, -1], np.int32)
 
         def host_step(s):
+            # the greedy agent's loop body (greedy.py:13-17) on the batched env: host arrays in, host arrays out
             if s % SPACING == 0:
                 c = env.cars_on_roads_flat()[:, :r].reshape(E, 4, I)
-                h_act.numpy()[:] = (np.tensordot(wts, c, axes=([0], [1])) < 0)
-            env.step_pinned(h_act, h_obs, h_rew, h_done)
+                np.less(np.tensordot(wts, c, axes=([0], [1])), 0, out=h_act.view(np.bool_))
+            obs, rew, done = env.step(h_act)
+            return float(rew[0, 0])  # the result is read on the host
 
         for s in range(max(3, min(a.warmup, 5))):
             host_step(s)
@@ -335,8 +333,8 @@ def b200_arm(a):
             dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
         e2e = {"value": float(e_vu.item()) / float(e_t.item()), "unit": "vehicle-updates/s",
                "h2d_bytes_per_step": int(E * I), "d2h_bytes_per_step": int(E * (OL * 4 + I * 4 + 1) + E * R * 4 // SPACING),
-               "steps": ne, "api": "VecTrafficEnv.step_pinned -> te_step(TE_HOST) with pinned host buffers; "
-               "greedy actions from cars_on_roads() on the host every %d steps" % SPACING}
+               "steps": ne, "api": "VecTrafficEnv.step(actions) -> te_step(TE_HOST): actions H2D, obs/reward/done D2H into the env's "
+               "page-locked host buffers every step; greedy actions from cars_on_roads() (D2H) on the host every %d steps" % SPACING}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

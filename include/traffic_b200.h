@@ -160,6 +160,11 @@ int te_get_trip_times(te_handle *h, int32_t *env_out, float *trip_out, int64_t c
 
 int te_synchronize(te_handle *h);
 
+/* Page-locked host memory for the TE_HOST entry points (so their copies run at full PCIe rate and
+   asynchronously to the launch); plain cudaHostAlloc / cudaFreeHost behind a C signature. */
+int te_host_alloc(uint64_t bytes, void **out);
+int te_host_free(void *ptr);
+
 /* Kernel time of the last te_step/te_step_raw launch in milliseconds (CUDA events on the launch stream). */
 int te_last_kernel_ms(te_handle *h, float *ms);
 

@@ -575,6 +575,17 @@ extern "C" int te_synchronize(te_handle *h) {
   return 0;
 }
 
+extern "C" int te_host_alloc(uint64_t bytes, void **out) {
+  if (!out) return fail("te_host_alloc: null argument");
+  CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+
+extern "C" int te_host_free(void *ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return 0;
+}
+
 extern "C" int te_last_kernel_ms(te_handle *h, float *ms) {
   if (!h || !ms) return fail("te_last_kernel_ms: null argument");
   if (!h->timed) return fail("te_last_kernel_ms: no step has been launched");

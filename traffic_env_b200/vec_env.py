@@ -80,15 +80,32 @@ class VecTrafficEnv(object):
         check(L.te_get_topology(self._h, self.dest.ctypes.data, self.nexts.ctypes.data, self.phases.ctypes.data,
                                 self.entrypoints.ctypes.data))
         E, I = self.num_envs, self.intersections
-        self._obs = np.empty((E, self.obs_len), np.float32)
-        self._obs_raw = np.empty((E, self.obs_raw_len), np.int32)
-        self._reward = np.empty((E, I), np.float32)
-        self._done = np.empty(E, np.uint8)
+        # result / action buffers live in page-locked host memory owned by this object
+        self._pinned = []
+        self._obs = self._host_array((E, self.obs_len), np.float32)
+        self._obs_raw = self._host_array((E, self.obs_raw_len), np.int32)
+        self._reward = self._host_array((E, I), np.float32)
+        self._done = self._host_array((E,), np.uint8)
+        self._act = self._host_array((E, I), np.uint8)
+        self._cars = self._host_array((E, self.roads), np.int32)
+
+    def _host_array(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        check(self._L.te_host_alloc(max(n, 16), C.byref(ptr)))
+        self._pinned.append(ptr)
+        buf = (C.c_ubyte * max(n, 16)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.te_destroy(self._h)
             self._h = C.c_void_p()
+            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars"):
+                setattr(self, name, None)
+            for ptr in self._pinned:
+                self._L.te_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -99,8 +116,10 @@ class VecTrafficEnv(object):
     # ------------------------------------------------------------ helpers
     def _actions(self, actions):
         a = np.asarray(actions)
-        a = np.ascontiguousarray(a.astype(bool).reshape(self.num_envs, self.intersections), dtype=np.uint8)
-        return a
+        if a.dtype != np.bool_ and a.dtype != np.uint8:
+            a = a.astype(bool)
+        np.not_equal(a.reshape(self.num_envs, self.intersections), 0, out=self._act.view(np.bool_))
+        return self._act
 
     # ------------------------------------------------------------ reference API, batched
     def reset(self, mask=None, init_phase=None):
@@ -168,9 +187,8 @@ class VecTrafficEnv(object):
         return out
 
     def cars_on_roads_flat(self):
-        out = np.empty((self.num_envs, self.roads), np.int32)
-        check(self._L.te_cars_on_roads(self._h, out.ctypes.data, TE_HOST, None))
-        return out
+        check(self._L.te_cars_on_roads(self._h, self._cars.ctypes.data, TE_HOST, None))
+        return self._cars
 
     def cars_on_roads(self):
         """[E, m, n, 4] like TrafficEnv.cars_on_roads (traffic_env.py:255-257)."""
