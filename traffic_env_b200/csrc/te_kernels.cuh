@@ -287,22 +287,39 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           }
         }
       }
-    } else if (p.arrival_mode == ARR_PHILOX && lane == 0) {
-      uint32_t draw = es->ph_draw, skip = es->ph_skip;
+    } else if (p.arrival_mode == ARR_PHILOX) {
+      // The gap process is sequential (k empty ticks, a car, a new gap ...) but its draws are counter-based:
+      // draw d arrives at tick skip0 + sum of the gaps of the draws before it.  32 draws per round, one per
+      // lane, exclusive prefix sum of the gaps, until a draw lands past the K ticks of this launch.
+      // snap[T] = (draw, skip) state after T ticks, written by the lane whose car is the next one due.
+      uint32_t draw0 = es->ph_draw;
+      long long tbase = es->ph_skip;          // arrival tick of draw `draw0`
+      long long prev = 0;                     // arrival tick of the draw before draw0 (ticks <= prev are settled)
       const uint32_t k0 = p.seed, k1 = (uint32_t)(p.env_id_base + env);
-      for (int t = 0; t < p.K; t++) {
-        s.snap[2 * t] = draw; s.snap[2 * t + 1] = skip;
-        for (;;) {
-          if (skip > 0) { skip--; break; }
-          uint32_t o[4];
-          philox4x32_10(draw, 0, 0, 0, k0, k1, o);
-          draw++;
-          const int idx = (int)__umulhi(o[1], (uint32_t)p.n_entry);
-          if (s.cnt[t * p.n_entry + idx] < 255) s.cnt[t * p.n_entry + idx]++;
-          skip = gap_from_u32(p.gap_cdf, p.n_gap, o[0]);
+      if (lane == 0) { s.snap[0] = draw0; s.snap[1] = (uint32_t)tbase; }
+      for (;;) {
+        uint32_t o[4];
+        philox4x32_10(draw0 + lane, 0, 0, 0, k0, k1, o);
+        const int gap = (int)gap_from_u32(p.gap_cdf, p.n_gap, o[0]);
+        int incl = gap;
+#pragma unroll
+        for (int sh = 1; sh < 32; sh <<= 1) { const int y = __shfl_up_sync(FULL, incl, sh); if (lane >= sh) incl += y; }
+        const long long tick = tbase + incl - gap;              // arrival tick of my draw
+        long long before = __shfl_up_sync(FULL, tick, 1);
+        if (lane == 0) before = prev;
+        if (tick < p.K) {
+          const int idx = (int)__umulhi(o[1], (uint32_t)p.n_entry) + (int)tick * p.n_entry;
+          atomicAdd(reinterpret_cast<unsigned int *>(s.cnt) + (idx >> 2), 1u << ((idx & 3) * 8));
         }
+        // after T ticks, for before < T <= tick (and T <= K), my draw is the next car: skip = tick - T
+        for (long long T = (before + 1 > 1 ? before + 1 : 1); T <= tick && T <= p.K; T++) {
+          s.snap[2 * T] = draw0 + lane; s.snap[2 * T + 1] = (uint32_t)(tick - T);
+        }
+        const long long last = __shfl_sync(FULL, tick, 31);
+        const long long next_base = __shfl_sync(FULL, tbase + incl, 31);
+        if (last >= p.K) break;
+        draw0 += 32; tbase = next_base; prev = last;
       }
-      s.snap[2 * p.K] = draw; s.snap[2 * p.K + 1] = skip;
     }
   }
   __syncthreads();
@@ -369,17 +386,20 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       const float lxj = __shfl_sync(FULL, leadx, j);
       float xn = 0.f, vn = 0.f;
       bool pw = false, pdet = false;
-      int o = 0;
+      int o = 0, slot = 1;
+      const int rbase = (j * nwarps + warp) * CAP;
       if (valid) {
         const int tt = ldj + k;
-        const int slot = tt < RING ? tt + 1 : tt - (RING - 1);   // ((ld + k) mod 19) + 1
-        const int rbase = (j * nwarps + warp) * CAP;
+        slot = tt < RING ? tt + 1 : tt - (RING - 1);         // ((ld + k) mod 19) + 1
         o = rbase + slot;
-        float x = s.xs[o], v = s.vs[o];
-        float xl = lxj, vl = 0.f, ll = 0.f;                  // virtual leader: v = 0, l = 0
-        if (k > 0) { const int lo = rbase + (slot == 1 ? RING : slot - 1); xl = s.xs[lo]; vl = s.vs[lo]; ll = c.len; }
-        idm_update(c, s.tabs, xl, vl, ll, x, v);
-        xn = x; vn = v;
+        xn = s.xs[o]; vn = s.vs[o];
+      }
+      // the car ahead is the previous item of the list: the lane below me, or (lane 0) one shared-memory read
+      float xl = __shfl_up_sync(FULL, xn, 1), vl = __shfl_up_sync(FULL, vn, 1), ll = c.len;
+      if (valid) {
+        if (k == 0) { xl = lxj; vl = 0.f; ll = 0.f; }        // virtual leader: v = 0, l = 0
+        else if (lane == 0) { const int lo = rbase + (slot == 1 ? RING : slot - 1); xl = s.xs[lo]; vl = s.vs[lo]; }
+        idm_update(c, s.tabs, xl, vl, ll, xn, vn);
         // wrapped ring, low segment: the reference tests x, not v (traffic_env.py:210)
         const bool lowseg = ldj > lcj && slot <= lcj;
         pw = (double)(lowseg ? xn : vn) < 0.2;
