@@ -86,6 +86,7 @@ typedef struct te_stats {
   double return_sum;         /* sum over closed episodes of sum_t mean_i reward (util.py:75) */
   double disc_return_sum;    /* same with gamma^t weighting */
   uint64_t seq_fallback_ticks; /* env-ticks whose transfer phase ran in strict road order */
+  uint64_t cars_exited;      /* cars that drove off an exit road (generated = live + exited + dropped) */
 } te_stats;
 
 typedef struct te_handle te_handle;

@@ -542,7 +542,7 @@ extern "C" int te_get_stats(te_handle *h, te_stats *out) {
   CU(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
   out->ticks = s.ticks; out->actor_steps = s.actor_steps; out->vehicle_updates = s.vehicle_updates;
   out->overflows = s.overflows; out->cars_generated = s.cars_generated; out->episodes = s.episodes;
-  out->return_sum = s.return_sum; out->disc_return_sum = s.disc_return_sum; out->seq_fallback_ticks = s.seq_fallback_ticks;
+  out->return_sum = s.return_sum; out->disc_return_sum = s.disc_return_sum; out->seq_fallback_ticks = s.seq_fallback_ticks; out->cars_exited = s.cars_exited;
   return 0;
 }
 

@@ -56,7 +56,8 @@ struct EnvScalars {
 };
 
 struct DeviceStats {
-  unsigned long long ticks, actor_steps, vehicle_updates, overflows, cars_generated, episodes, seq_fallback_ticks;
+  unsigned long long ticks, actor_steps, vehicle_updates, overflows, cars_generated, episodes, seq_fallback_ticks,
+      cars_exited;
   double return_sum, disc_return_sum;
 };
 
@@ -196,7 +197,7 @@ struct Smem {
   int *wait, *elapsed, *ovf;
   unsigned long long *mbar;
   uint32_t *snap;
-  int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks
+  int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks, [6] cars that left the map
   uint8_t *items, *phase, *act, *pdst, *cnt;
   PowfTables *tabs;
 };
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     s.phase[i] = (uint8_t)ph; s.act[i] = (uint8_t)act; s.elapsed[i] = el;
     s.pdst[i] = p.passed_dst[(size_t)env * p.I + i]; s.ovf[i] = 0;
   }
-  if (tid == 0) { s.misc[0] = 0x7fffffff; s.misc[1] = -1; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; }
+  if (tid == 0) { s.misc[0] = 0x7fffffff; s.misc[1] = -1; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; s.misc[6] = 0; }
   if (warp == 0) {
     // arrivals of the K ticks as per-tick, per-entry-road counts (cars are identical, so the
     // order of arrivals within a tick only matters per road, where it is preserved)
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   __syncthreads();
 
   const IdmConst c = p.idm;
-  int veh_local = 0, gen_local = 0;
+  int veh_local = 0, gen_local = 0, exit_local = 0;
   int t = 0;
   for (; t < p.K; t++) {
     // ---------------------------------------------------------------- phase A
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           }
         }
         ld = f;
+        if (nxt < 0) exit_local += npop;                // cars leaving the map
         if (nxt >= 0) {
           passed += npop;                               // traffic_env.py:127
           s.pdst[dst] = 1;                              // :128
@@ -493,8 +495,9 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   for (int o = 16; o > 0; o >>= 1) {
     veh_local += __shfl_xor_sync(FULL, veh_local, o);
     gen_local += __shfl_xor_sync(FULL, gen_local, o);
+    exit_local += __shfl_xor_sync(FULL, exit_local, o);
   }
-  if (lane == 0) { atomicAdd(&s.misc[2], veh_local); atomicAdd(&s.misc[4], gen_local); }
+  if (lane == 0) { atomicAdd(&s.misc[2], veh_local); atomicAdd(&s.misc[4], gen_local); atomicAdd(&s.misc[6], exit_local); }
   s.wait[my_road] = wait;
   __syncthreads();
 
@@ -572,6 +575,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (s.misc[3]) atomicAdd(&p.stats->overflows, (unsigned long long)s.misc[3]);
     atomicAdd(&p.stats->cars_generated, (unsigned long long)s.misc[4]);
     if (s.misc[5]) atomicAdd(&p.stats->seq_fallback_ticks, (unsigned long long)s.misc[5]);
+    if (s.misc[6]) atomicAdd(&p.stats->cars_exited, (unsigned long long)s.misc[6]);
     bulk_commit_wait();  // the flush has left shared memory and reached HBM before the CTA retires
   }
 }

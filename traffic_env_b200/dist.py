@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 STAT_KEYS = ("ticks", "actor_steps", "vehicle_updates", "overflows", "cars_generated", "episodes",
-             "return_sum", "disc_return_sum", "seq_fallback_ticks")
+             "return_sum", "disc_return_sum", "seq_fallback_ticks", "cars_exited")
 
 
 def shard_range(total_envs, rank, world):
