@@ -345,6 +345,8 @@ def b200_arm(a):
                "sample": "1 env of %s on 1 core (oracle/traffic_oracle.c): 60-actor-step pre-roll, then %.0f s of "
                "actor steps (%d steps)" % (a.workload, r1["seconds"], r1["actor_steps"])}
 
+    barrier()
+    flush_gbs = env.stage_bandwidth(5) if rank == 0 else None
     arith_peak = None
     if rank == 0:
         from traffic_env_b200.vec_env import idm_arithmetic_peak
@@ -367,6 +369,9 @@ def b200_arm(a):
                          "algorithmic_bytes_per_env_step": bytes_env, "cars_per_env": cars_env,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "the fused K-tick kernel is issue/FP64-pipe bound, not HBM bound (SURVEY.md 8d); see roofline_issue"},
+            "roofline_flush": {"bound": "hbm", "achieved": flush_gbs, "peak": peak, "unit": "GB/s", "frac": flush_gbs / peak,
+                               "what": "the step kernel's bulk-TMA stage-in + flush alone (te_stage_kernel: same CTA shape "
+                               "and shared-memory footprint, no ticks), read + written bytes"},
             "roofline_compute": {"bound": "idm arithmetic (registers only, all lanes busy: te_idm_peak micro-kernel)",
                                  "achieved": float(np.mean(kvu)) / (k_ms * 1e-3), "peak": arith_peak,
                                  "unit": "vehicle-updates/s", "frac": float(np.mean(kvu)) / (k_ms * 1e-3) / arith_peak},

@@ -169,6 +169,11 @@ int te_host_free(void *ptr);
 /* Kernel time of the last te_step/te_step_raw launch in milliseconds (CUDA events on the launch stream). */
 int te_last_kernel_ms(te_handle *h, float *ms);
 
+/* HBM bandwidth (GB/s, read + written bytes) of the step kernel's stage-in + flush alone: the same bulk-TMA
+   copies with the same CTA shape and shared-memory footprint, no ticks in between.  The state is rewritten
+   unchanged.  Used by bench.py to report what the flush achieves against the HBM peak. */
+int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_per_sec);
+
 /* Arithmetic-only ceiling of the path: vehicle-updates/s of a micro-kernel in which every lane of a fully
    occupied GPU does nothing but dependent IDM updates (traffic_env.py:50-62) in registers.  Used by bench.py
    as the compute roofline of the step kernel. */

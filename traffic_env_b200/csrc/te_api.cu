@@ -575,6 +575,28 @@ extern "C" int te_synchronize(te_handle *h) {
   return 0;
 }
 
+extern "C" int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_per_sec) {
+  if (!h || !gbytes_per_sec || repeats < 1) return fail("te_stage_bandwidth: bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
+  const SmemLayout L = make_layout(h->Rp, h->I, 10, h->n_entry, validate);
+  CU(cudaFuncSetAttribute(te_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  StepParams p = h->base;
+  p.K = 10;
+  te_stage_kernel<<<h->cfg.num_envs, h->Rp, L.total, h->stream>>>(p, validate);  // warm-up (state is rewritten unchanged)
+  CU(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < repeats; i++) te_stage_kernel<<<h->cfg.num_envs, h->Rp, L.total, h->stream>>>(p, validate);
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  const double bytes = 2.0 /* planes */ * 2.0 /* in + out */ * (double)h->cfg.num_envs * h->Rp * CAP * 4.0 * repeats;
+  *gbytes_per_sec = bytes / (ms * 1e-3) / 1e9;
+  return 0;
+}
+
 extern "C" int te_host_alloc(uint64_t bytes, void **out) {
   if (!out) return fail("te_host_alloc: null argument");
   CU(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));

@@ -580,6 +580,32 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   }
 }
 
+// Staging only: the step kernel's bulk-TMA stage-in and flush of one env's ring planes with no ticks in
+// between (same CTA shape and shared-memory footprint, so the same number of copies is in flight per SM).
+// Measures the HBM bandwidth the load/flush phases of te_step_kernel run at.
+__global__ void te_stage_kernel(const StepParams p, int validate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry, validate != 0);
+  const Smem s = carve(smem_raw, L);
+  const int env = blockIdx.x;
+  const uint32_t plane_bytes = (uint32_t)p.Rp * CAP * 4;
+  if (threadIdx.x == 0) {
+    mbar_init(s.mbar, 1);
+    fence_proxy_async();
+    mbar_expect_tx(s.mbar, plane_bytes * 2u);
+    bulk_load(s.xs, p.x + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+    bulk_load(s.vs, p.v + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+  }
+  __syncthreads();
+  mbar_wait(s.mbar, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bulk_store(p.x + (size_t)env * p.Rp * CAP, s.xs, plane_bytes);
+    bulk_store(p.v + (size_t)env * p.Rp * CAP, s.vs, plane_bytes);
+    bulk_commit_wait();
+  }
+}
+
 // TrafficEnv._reset (traffic_env.py:259-272) on the HBM state.  mask == nullptr: every env;
 // use_done != 0: envs whose last actor step ended the episode (TE_AUTO_RESET).
 __global__ void te_reset_kernel(StepParams p, const uint8_t *mask, const uint8_t *init_phase, int use_done) {

@@ -242,6 +242,12 @@ class VecTrafficEnv(object):
         check(self._L.te_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def stage_bandwidth(self, repeats=5):
+        """GB/s of the step kernel's bulk-TMA stage-in + flush with no ticks in between (te_stage_bandwidth)."""
+        out = C.c_double()
+        check(self._L.te_stage_bandwidth(self._h, int(repeats), C.byref(out)))
+        return out.value
+
     def synchronize(self):
         check(self._L.te_synchronize(self._h))
 
