@@ -306,15 +306,15 @@ def b200_arm(a):
     e2e = None
     if not a.no_e2e:
         h_act = np.zeros((E, I), dtype=np.uint8)
-        wts = np.array([1, 1, -1, -1], np.int32)
 
         def host_step(s):
-            # the greedy agent's loop body (greedy.py:13-17) on the batched env: host arrays in, host arrays out
+            # greedy agent loop (greedy.py:13-17) on the batched env through the public host API: every `spacing`
+            # steps the controller output comes back to the host (te_greedy_actions, D2H); every step the actions
+            # go host -> device and obs / reward / done come device -> host.
             if s % SPACING == 0:
-                c = env.cars_on_roads_flat()[:, :r].reshape(E, 4, I)
-                np.less(np.tensordot(wts, c, axes=([0], [1])), 0, out=h_act.view(np.bool_))
+                h_act[:] = env.greedy_actions()
             obs, rew, done = env.step(h_act)
-            return float(rew[0, 0])  # the result is read on the host
+            return float(rew[0, 0]) + float(obs[0, 0])  # the result is read on the host
 
         for s in range(max(3, min(a.warmup, 5))):
             host_step(s)
@@ -332,9 +332,9 @@ def b200_arm(a):
             dist.all_reduce(e_vu, op=dist.ReduceOp.SUM)
             dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
         e2e = {"value": float(e_vu.item()) / float(e_t.item()), "unit": "vehicle-updates/s",
-               "h2d_bytes_per_step": int(E * I), "d2h_bytes_per_step": int(E * (OL * 4 + I * 4 + 1) + E * R * 4 // SPACING),
+               "h2d_bytes_per_step": int(E * I), "d2h_bytes_per_step": int(E * (OL * 4 + I * 4 + 1) + E * I // SPACING),
                "steps": ne, "api": "VecTrafficEnv.step(actions) -> te_step(TE_HOST): actions H2D, obs/reward/done D2H into the env's "
-               "page-locked host buffers every step; greedy actions from cars_on_roads() (D2H) on the host every %d steps" % SPACING}
+               "page-locked host buffers every step; VecTrafficEnv.greedy_actions() (device controller, actions D2H) every %d steps" % SPACING}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
