@@ -227,6 +227,10 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (cfg->arrival_mode == TE_ARRIVALS_PHILOX && (cdf.empty() || h->n_entry == 0)) {
     free_handle(h); return fail("te_create: Philox arrivals need cars_per_tick > 0 and at least one entry road");
   }
+  if (cfg->arrival_mode == TE_ARRIVALS_PHILOX && cfg->cars_per_tick > 16.0 * h->n_entry) {
+    // per-tick per-road arrival counts are 8-bit; a ring holds 18 cars anyway
+    free_handle(h); return fail("te_create: cars_per_tick %.1f is beyond what %d entry roads can take", cfg->cars_per_tick, h->n_entry);
+  }
   CUH(dalloc(&h->d_gap_cdf, cdf.size()));
   if (!cdf.empty()) CUH(cudaMemcpy(h->d_gap_cdf, cdf.data(), cdf.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
@@ -336,7 +340,11 @@ extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16
   const int64_t total = offsets[no - 1];
   for (size_t e = 0; e < E; e++)
     for (int t = 0; t < horizon; t++)
-      if (offsets[e * (horizon + 1) + t] > offsets[e * (horizon + 1) + t + 1]) return fail("te_set_arrivals: offsets not monotone");
+    {
+      const int64_t a0 = offsets[e * (horizon + 1) + t], a1 = offsets[e * (horizon + 1) + t + 1];
+      if (a0 > a1) return fail("te_set_arrivals: offsets not monotone");
+      if (a1 - a0 > 255) return fail("te_set_arrivals: more than 255 arrivals in one tick of one env");
+    }
   std::vector<signed char> is_entry(h->R, 0);
   for (int rd : h->entry) is_entry[rd] = 1;
   for (int64_t k = 0; k < total; k++)

@@ -6,9 +6,9 @@
 // as two float planes x[Rp][20], v[Rp][20] - every car has the same archetype
 // (traffic_env.py:35-43), so x and v are the only dynamic fields - and flushed once.
 //
-// Roads map to warps: lane l of warp w owns road l * nwarps + w for the whole launch (interleaved, so
-// every warp gets the same mix of entry, interior and exit roads and the two CTA barriers of a tick
-// wait on balanced warps); the road's ring indices and counters live in that lane's registers.
+// Roads map to warps: every lane owns one road for the whole launch; the road's ring indices and counters
+// live in that lane's registers.  The assignment is rebuilt per launch from the car counts (counting sort +
+// snake deal) so the warps carry even loads between the two CTA barriers of a tick.
 //
 // Per tick (order of traffic_env.py:224-248, see DESIGN.md "tick phases"):
 //   phase A  (warp-local, no CTA barrier inside)
@@ -326,9 +326,32 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   __syncthreads();
   mbar_wait(s.mbar, 0);  // the ring planes have landed
 
-  // ---- lane = road: ring indices, counters and topology of my road live in registers
+  // ---- road -> (warp, lane) assignment for this launch, balanced by car count: counting sort of the roads by
+  // their current number of cars (0..18), then dealt to the warps in snake order, so every warp simulates
+  // nearly the same number of cars per tick and the two CTA barriers of a tick wait on even warps.
+  // Any bijection gives the same results (the update is per car); only the waiting changes.
   const int nwarps = blockDim.x >> 5;            // blockDim.x == Rp
-  const int my_road = lane * nwarps + warp;
+  int my_road;
+  {
+    int *hist = reinterpret_cast<int *>(s.items);            // [0..19] counts, [20..39] tickets (items list is idle here)
+    short *owner = reinterpret_cast<short *>(s.items + 160);
+    for (int i = tid; i < 40; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint32_t w0 = __float_as_uint(s.xs[tid * CAP]);
+    const int n0 = ring_count(w0 & 0xff, (w0 >> 8) & 0xff);
+    atomicAdd(&hist[n0], 1);
+    __syncthreads();
+    int base = 0;
+    for (int c2 = RING - 1; c2 > n0; --c2) base += hist[c2];  // roads with more cars come first
+    const int rank = base + atomicAdd(&hist[20 + n0], 1);
+    const int row = rank / nwarps, pos = rank - row * nwarps;
+    const int w = (row & 1) ? nwarps - 1 - pos : pos;
+    owner[w * 32 + row] = (short)tid;
+    __syncthreads();
+    my_road = owner[tid];
+    __syncthreads();                                         // the items region is reused by the tick loop
+  }
+  // ---- lane = road: ring indices, counters and topology of my road live in registers
   const bool is_road = my_road < p.R, is_train = my_road < p.r;
   float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
   float *wr = VALIDATE ? s.ws + my_road * CAP : nullptr;
@@ -388,7 +411,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       float xn = 0.f, vn = 0.f;
       bool pw = false, pdet = false;
       int o = 0, slot = 1;
-      const int rbase = (j * nwarps + warp) * CAP;
+      const int rbase = __shfl_sync(FULL, my_road, j) * CAP;
       if (valid) {
         const int tt = ldj + k;
         slot = tt < RING ? tt + 1 : tt - (RING - 1);         // ((ld + k) mod 19) + 1
