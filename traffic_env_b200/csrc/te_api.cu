@@ -252,6 +252,8 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.idm.delta = a[4]; p.idm.v0 = a[5]; p.idm.T = a[7]; p.idm.s0 = a[8];
   { volatile float ab = a[3] * a[6]; p.idm.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
   p.idm.rcp_two_sqrt_ab = 1.0 / p.idm.two_sqrt_ab;
+  p.idm.v0_d = (double)a[5]; p.idm.rcp_v0 = 1.0 / (double)a[5];
+  p.idm.s0_d = (double)a[8]; p.idm.a_d = (double)a[3]; p.idm.rate_d = (double)cfg->rate; p.idm.delta_d = (double)a[4];
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
@@ -644,6 +646,8 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
   { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
   c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
+  c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
+  c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
@@ -663,6 +667,8 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
   { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
   c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
+  c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
+  c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
