@@ -82,6 +82,12 @@ static step_kernel_t step_kernel_for(int threads, bool validate) {
   return te_step_kernel<1024, 1, false>;
 }
 
+// The double literals of the IDM update live in constant memory (te_math.cuh: g_mc); one upload per device.
+static cudaError_t upload_math_consts() {
+  const MathConsts m = math_consts_host();
+  return cudaMemcpyToSymbol(g_mc, &m, sizeof(m));
+}
+
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
 
 extern "C" void te_default_config(te_config *c) {
@@ -163,6 +169,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->stream = nullptr; h->ev0 = h->ev1 = nullptr; h->timed = false; h->trip_cap = 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUH(cudaSetDevice(h->device));
+  CUH(upload_math_consts());
   const int m = cfg->m, n = cfg->n;
   h->V = m * n; h->I = h->V; h->r = 4 * h->V; h->R = h->r + 2 * n + 2 * m;
   h->Rp = (h->R + GROUP_ROADS - 1) / GROUP_ROADS * GROUP_ROADS;
@@ -642,6 +649,7 @@ extern "C" int te_test_powf(int device, const float *x, float y, float *out, int
 extern "C" int te_test_idm(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
                            const float *x, const float *v, float *x_out, float *v_out, int64_t n) {
   CU(cudaSetDevice(device));
+  CU(upload_math_consts());
   IdmConst c;
   c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
   { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
@@ -663,6 +671,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
 extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters, double *updates_per_sec) {
   if (!a || !updates_per_sec || iters < 1) return fail("te_idm_peak: bad argument");
   CU(cudaSetDevice(device));
+  CU(upload_math_consts());
   IdmConst c;
   c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
   { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
