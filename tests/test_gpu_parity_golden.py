@@ -144,3 +144,42 @@ def test_validate_mode_fused_steps_same_trips():
         assert not done[0]
     ta, tb = a.trip_times()[1], b.trip_times()[1]
     assert len(ta) > 20 and ta.tobytes() == tb.tobytes()
+
+
+def test_fused_learn_switch_matches_raw_ticks():
+    """learn_switch=True: the action toggles the phase on EVERY tick of the actor step (traffic_env.py:225-227);
+    the fused launch derives phase/elapsed of the later ticks in closed form - compare with K raw ticks."""
+    g = np.load(os.path.join(GOLDEN, "learnswitch_2x3.npz"))
+    sched = unpack_schedule(g["sched_off"], g["sched_roads"])
+    K = 7
+    a = make_env(g, remi=False)
+    b = make_env(g, remi=False, ticks_per_step=K)
+    for env in (a, b):
+        env.set_arrivals([sched])
+        env.reset(init_phase=g["init_phase"][None])
+    rng = np.random.RandomState(3)
+    checked = 0
+    for s in range(60):
+        act = rng.randint(2, size=(1, 6))
+        tot, done_raw, obs_passed = np.zeros(6, np.float32), False, np.zeros(24, np.float32)
+        for k in range(K):
+            o, r, d = a.step_raw(act)
+            tot += r[0]
+            obs_passed += o[0][:24]
+            if d[0]:
+                done_raw = True
+                break
+        if done_raw:
+            # the raw env stopped early like Repeater does; re-align the fused env on the same number of ticks
+            of, rf, df = b.step(act, k=k + 1)
+        else:
+            of, rf, df = b.step(act)
+        assert bool(df[0]) == done_raw
+        assert rf[0].tobytes() == tot.tobytes()
+        assert of[0][:24].tobytes() == obs_passed.tobytes()
+        sa, sb = a.get_state(), b.get_state()
+        for key in ("leading", "lastcar", "waiting", "passed_dst"):
+            assert (sa[key] == sb[key]).all(), (s, key)
+        assert (sa["obs"][0][24:] == sb["obs"][0][24:]).all(), s   # detected | phase | elapsed
+        checked += 1
+    assert checked == 60
