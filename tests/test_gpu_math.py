@@ -112,3 +112,36 @@ def test_philox_block_matches_oracle():
     out = np.empty(4, np.uint32)
     m.check(L.te_test_philox(0, z.ctypes.data, z[:2].ctypes.data, out.ctypes.data))
     assert [hex(int(v)) for v in out] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+def test_idm_adversarial_operands():
+    """The branch-free fast path and its generic fallback against the oracle on operands chosen to hit the
+    acceptance tests of the division, the underflow / subnormal branches of powf and non-finite state."""
+    rng = np.random.RandomState(21)
+    n = 6_000_000
+    arch = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], np.float32)
+    x = rng.uniform(-300, 600, n).astype(np.float32)
+    v = np.abs(rng.standard_normal(n) * 8).astype(np.float32)
+    vl = np.abs(rng.standard_normal(n) * 8).astype(np.float32)
+    ll = np.full(n, 4.0, np.float32)
+    # gaps over 30 orders of magnitude, both signs, and exact cancellations s + 1e-8 ~ 0
+    mag = np.exp(rng.uniform(np.log(1e-12), np.log(1e12), n))
+    s = (mag * rng.choice([-1.0, 1.0], n, p=[0.2, 0.8])).astype(np.float32)
+    xl = (x.astype(np.float64) + 4.0 + s).astype(np.float32)
+    k = n // 10
+    xl[:k] = x[:k] + np.float32(4.0)                      # s == 0 exactly
+    xl[k:2 * k] = (x[k:2 * k] + np.float32(4.0)) + np.float32(-1e-8)
+    v[2 * k:3 * k] = np.exp(rng.uniform(np.log(1e-45), np.log(1e-3), k)).astype(np.float32)   # creeping / subnormal speeds
+    v[3 * k:3 * k + 1000] = 0.0
+    v[3 * k + 1000:3 * k + 2000] = np.float32(13.89)      # ratio exactly 1
+    v[3 * k + 2000:3 * k + 3000] = np.float32(1e30)       # overflowing power
+    special = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0, -0.0], np.float32)
+    idx = rng.randint(4 * k, n, size=30000)
+    x[idx[:10000]] = rng.choice(special, 10000)
+    v[idx[10000:20000]] = rng.choice(special, 10000)
+    xl[idx[20000:]] = rng.choice(special, 10000)
+    gx, gv = gpu_idm(0.5, arch, xl, vl, ll, x, v)
+    ox, ov = orc.sim_bulk(0.5, xl, vl, ll, x, v, arch)
+    bx, bv = ~same_bits(gx, ox), ~same_bits(gv, ov)
+    assert not bx.any() and not bv.any(), "x mismatches %d (first at %s), v mismatches %d" % (
+        bx.sum(), np.nonzero(bx)[0][:3], bv.sum())
