@@ -185,6 +185,11 @@ int te_test_powf(int device, const float *x, float y, float *out, int64_t n);
 /* One IDM update per element (traffic_env.py:50-62): follower (x,v) behind leader (xl,vl,ll). */
 int te_test_idm(int device, float rate, const float *archetype, const float *xl, const float *vl, const float *ll,
                 const float *x, const float *v, float *x_out, float *v_out, int64_t n);
+/* powf(r, 4) over every non-negative finite float r: out[0] = #r where RN_f32((r*r)*(r*r)) differs from the
+   glibc algorithm, out[1] = largest distance (2^-52 units of the significand) of such a product from the float
+   rounding boundary, out[2] = #r the shortcut filter with threshold tau declines, out[3] = #r it accepts although
+   the results differ (the proof obligation: must be 0). */
+int te_test_powf4_exhaustive(int device, uint64_t tau, uint64_t out[4]);
 /* Philox4x32-10 block: out[4] for counter ctr[4], key[2]. */
 int te_test_philox(int device, const uint32_t *ctr, const uint32_t *key, uint32_t *out);
 

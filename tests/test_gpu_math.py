@@ -145,3 +145,36 @@ def test_idm_adversarial_operands():
     bx, bv = ~same_bits(gx, ox), ~same_bits(gv, ov)
     assert not bx.any() and not bv.any(), "x mismatches %d (first at %s), v mismatches %d" % (
         bx.sum(), np.nonzero(bx)[0][:3], bv.sum())
+
+
+def test_powf4_filter_exhaustive():
+    """Proof by exhaustion of the delta == 4 shortcut: over EVERY non-negative finite float r, whenever the filter
+    accepts RN_f32((r*r)*(r*r)) it equals the glibc algorithm's result (which test_powf_* tie to the host libm)."""
+    L, m = _lib()
+    out = np.zeros(4, np.uint64)
+    m.check(L.te_test_powf4_exhaustive(0, 1 << 20, out.ctypes.data))
+    differ, max_dist, declined, accepted_but_wrong = (int(v) for v in out)
+    assert accepted_but_wrong == 0
+    assert 0 < differ < 1_000_000 and max_dist < (1 << 20)     # the shortcut is not vacuous and the margin holds
+    # results outside the normal float range (r < 2^-31.5 or r >= 2^32) are declined by construction; of the rest ~0.4 %
+    assert declined < 0.76 * 0x7f800000
+
+
+def test_idm_with_and_without_powf4_shortcut_agree():
+    """Same operands through a handle-independent hook with the shortcut disabled (environment switch)."""
+    import os
+    rng = np.random.RandomState(33)
+    n = 1_000_000
+    arch = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], np.float32)
+    x = rng.uniform(0, 250, n).astype(np.float32)
+    xl = (x + rng.uniform(4, 120, n)).astype(np.float32)
+    v = rng.uniform(0, 15, n).astype(np.float32)
+    vl = rng.uniform(0, 15, n).astype(np.float32)
+    ll = np.full(n, 4, np.float32)
+    a = gpu_idm(0.5, arch, xl, vl, ll, x, v)
+    os.environ["TE_NO_POWF4_SHORTCUT"] = "1"
+    try:
+        b = gpu_idm(0.5, arch, xl, vl, ll, x, v)
+    finally:
+        del os.environ["TE_NO_POWF4_SHORTCUT"]
+    assert same_bits(a[0], b[0]).all() and same_bits(a[1], b[1]).all()

@@ -261,6 +261,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.idm.rcp_two_sqrt_ab = 1.0 / p.idm.two_sqrt_ab;
   p.idm.v0_d = (double)a[5]; p.idm.rcp_v0 = 1.0 / (double)a[5];
   p.idm.s0_d = (double)a[8]; p.idm.a_d = (double)a[3]; p.idm.rate_d = (double)cfg->rate; p.idm.delta_d = (double)a[4];
+  p.idm.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
@@ -656,6 +657,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
   c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
   c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
+  c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
@@ -678,6 +680,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
   c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
   c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
+  c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
@@ -695,6 +698,19 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaEventElapsedTime(&ms, e0, e1));
   *updates_per_sec = (double)threads * blocks * iters / (ms * 1e-3);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  return 0;
+}
+
+extern "C" int te_test_powf4_exhaustive(int device, uint64_t tau, uint64_t out[4]) {
+  if (!out) return fail("te_test_powf4_exhaustive: null argument");
+  CU(cudaSetDevice(device));
+  unsigned long long *d = nullptr;
+  CU(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+  CU(cudaMemset(d, 0, 4 * sizeof(unsigned long long)));
+  te_powf4_exhaustive_kernel<<<148 * 16, 256>>>((unsigned long long)tau, d);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return 0;
 }
 

@@ -747,6 +747,28 @@ __global__ void te_idm_peak_kernel(IdmConst c, int iters, float *sink) {
   sink[gid] = x + v;
 }
 
+// Exhaustive study of powf(r, 4) over EVERY non-negative finite float r: compares glibc's algorithm with
+// RN_f32((r*r)*(r*r)) (double products) and records, for the inputs where they differ, how far the double
+// r^4 sits from the float rounding boundary (in units of 2^-52 of the significand).  out[0] = #inputs where the
+// two differ, out[1] = max boundary distance among them, out[2] = #inputs the filter (distance <= tau or result
+// outside the normal float range) sends to the full algorithm, out[3] = #inputs where the filter accepts but the
+// results differ (must be 0).
+__global__ void te_powf4_exhaustive_kernel(unsigned long long tau, unsigned long long *out) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long diff = 0, maxd = 0, slow = 0, bad = 0;
+  for (unsigned long long ix = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ix < 0x7f800000ull; ix += stride) {
+    const float r = __uint_as_float((uint32_t)ix);
+    const float ref = powf_glibc(r, 4.0f, &g_powf_tables);
+    float fast;
+    unsigned dist;
+    const bool acc = powf4_try(r, (unsigned)tau, fast, dist);
+    const bool same = __float_as_uint(fast) == __float_as_uint(ref);
+    if (!same) { diff++; if (acc) bad++; if (dist > maxd && dist != 0xffffffffu) maxd = dist; }
+    if (!acc) slow++;
+  }
+  atomicAdd(&out[0], diff); atomicMax(&out[1], maxd); atomicAdd(&out[2], slow); atomicAdd(&out[3], bad);
+}
+
 __global__ void te_test_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
   uint32_t o[4];
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);
