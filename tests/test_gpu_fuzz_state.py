@@ -63,7 +63,7 @@ def load_oracle(o, st):
 @pytest.mark.parametrize("m,n,L,E,dense,ordered", [
     (3, 3, 250.0, 96, True, False), (3, 3, 250.0, 96, False, False), (3, 3, 250.0, 64, True, True),
     (2, 3, 100.0, 64, True, False), (1, 1, 60.0, 32, True, False), (10, 10, 500.0, 6, True, False),
-    (4, 2, 80.0, 48, False, True)])
+    (4, 2, 80.0, 48, False, True), (3, 2, 123.456, 64, True, False), (2, 2, 77.7, 48, True, False)])
 def test_random_states_tick_by_tick(m, n, L, E, dense, ordered):
     from traffic_env_b200 import VecTrafficEnv
     rng = np.random.RandomState(1000 * m + 10 * n + int(dense) + 2 * int(ordered))

@@ -252,6 +252,11 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   StepParams &p = h->base;
   p.V = h->V; p.r = h->r; p.R = h->R; p.Rp = h->Rp; p.I = h->I; p.n_entry = h->n_entry; p.G = h->G;
   p.num_envs = cfg->num_envs; p.length = cfg->length; p.det_thr = (double)cfg->length - 10.0;
+  {
+    float f = (float)p.det_thr;                       // round to nearest, then step down if that went above
+    if ((double)f > p.det_thr) f = nextafterf(f, -INFINITY);
+    p.det_thr_f = f;
+  }
   p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
   p.gamma = cfg->gamma;
   const float *a = cfg->archetype;

@@ -38,7 +38,7 @@ constexpr int CAP = 20;            // CAPACITY, traffic_env.py:24
 constexpr int RING = CAP - 1;      // live ring positions 1..19
 constexpr int YELLOW_TICKS = 6;    // traffic_env.py:21
 constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
-constexpr int WARP_ITEMS = 640;    // per-warp compaction list: 32 roads * 18 cars = 576 entries, padded
+constexpr int WARP_ITEMS = 1280;   // per-warp compaction list: 32 roads * 18 cars = 576 two-byte entries, padded
 constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
@@ -74,6 +74,7 @@ struct StepParams {
   int num_envs;
   float length;
   double det_thr;         // (double)length - 10.0  (traffic_env.py:201: float32 - int64 types as float64)
+  float det_thr_f;        // largest float <= det_thr: for every float x, (double)x > det_thr  <=>  x > det_thr_f
   int flags, arrival_mode, K, raw, episode_len;
   float gamma;
   IdmConst idm;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   const int nxt = p.nexts[my_road], upr = p.up[my_road], ei = p.entry_idx[my_road];
   const int dst = is_train ? my_road % p.V : 0;
   const int road_phase = (my_road / p.V) < 2;
-  uint8_t *items = s.items + warp * WARP_ITEMS;
+  unsigned short *items = reinterpret_cast<unsigned short *>(s.items + warp * WARP_ITEMS);
   __syncthreads();
 
   const IdmConst c = p.idm;
@@ -398,15 +399,15 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
     const int start = incl - n;
     const int total = __shfl_sync(FULL, incl, 31);
-    for (int k = 0; k < n; k++) items[start + k] = (uint8_t)lane;
+    for (int k = 0; k < n; k++) items[start + k] = (unsigned short)(lane | (k << 8));  // owning lane, car index
     __syncwarp();
     int wacc = 0, dacc = 0;
     for (int ch = (total + 31) / 32 - 1; ch >= 0; --ch) {
       const int ci = ch * 32 + lane;
       const bool valid = ci < total;
-      const int j = valid ? items[ci] : 0;                 // owning road lane
+      const int it = valid ? items[ci] : 0;
+      const int j = it & 31, k = it >> 8;                  // owning road lane, k-th car from the front of its road
       const int ldj = __shfl_sync(FULL, ld, j), lcj = __shfl_sync(FULL, lc, j);
-      const int k = ci - __shfl_sync(FULL, start, j);      // k-th car from the front of its road
       const float lxj = __shfl_sync(FULL, leadx, j);
       float xn = 0.f, vn = 0.f;
       bool pw = false, pdet = false;
@@ -420,14 +421,19 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       }
       // the car ahead is the previous item of the list: the lane below me, or (lane 0) one shared-memory read
       float xl = __shfl_up_sync(FULL, xn, 1), vl = __shfl_up_sync(FULL, vn, 1), ll = c.len;
+      // lane 0's predecessor sits in the next lower chunk: one predicated shared-memory read instead of the shuffle
+      const int lo0 = rbase + (slot == 1 ? RING : slot - 1);
+      const bool from_smem = valid && lane == 0 && k > 0;
+      if (from_smem) { xl = s.xs[lo0]; vl = s.vs[lo0]; }
+      if (k == 0) { xl = lxj; vl = 0.f; ll = 0.f; }          // virtual leader: v = 0, l = 0
       if (valid) {
-        if (k == 0) { xl = lxj; vl = 0.f; ll = 0.f; }        // virtual leader: v = 0, l = 0
-        else if (lane == 0) { const int lo = rbase + (slot == 1 ? RING : slot - 1); xl = s.xs[lo]; vl = s.vs[lo]; }
         idm_update(c, s.tabs, xl, vl, ll, xn, vn);
         // wrapped ring, low segment: the reference tests x, not v (traffic_env.py:210)
         const bool lowseg = ldj > lcj && slot <= lcj;
-        pw = (double)(lowseg ? xn : vn) < 0.2;
-        pdet = (double)xn > p.det_thr;
+        // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
+        // float w: (double)w < 0.2  <=>  w < 0.2f.  Same for the detector threshold with det_thr_f (see StepParams).
+        pw = (lowseg ? xn : vn) < 0.2f;
+        pdet = xn > p.det_thr_f;
       }
       const uint32_t bw = __ballot_sync(FULL, pw), bd = __ballot_sync(FULL, pdet);
       __syncwarp();  // every lane has read its leader before any lane overwrites a slot (Jacobi update)
