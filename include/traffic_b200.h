@@ -190,6 +190,9 @@ int te_test_idm(int device, float rate, const float *archetype, const float *xl,
    rounding boundary, out[2] = #r the shortcut filter with threshold tau declines, out[3] = #r it accepts although
    the results differ (the proof obligation: must be 0). */
 int te_test_powf4_exhaustive(int device, uint64_t tau, uint64_t out[4]);
+/* v / cst for every non-negative finite float v: out[0] = #v where the multiply + 2 FMA sequence differs from
+   the IEEE quotient, out[1] = those with a normal quotient, out[2] = bits of the largest such v. */
+int te_test_fdiv_const_exhaustive(int device, float cst, uint64_t out[3]);
 /* Philox4x32-10 block: out[4] for counter ctr[4], key[2]. */
 int te_test_philox(int device, const uint32_t *ctr, const uint32_t *key, uint32_t *out);
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "te_default_config", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
     "te_reset", "te_set_arrivals", "te_step", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
     "te_greedy_actions", "te_get_state", "te_set_state", "te_get_stats", "te_get_trip_times",
-    "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_philox",
+    "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_fdiv_const_exhaustive", "te_test_philox",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
     L.te_test_powf.argtypes = [C.c_int, vp, C.c_float, vp, i64]
     L.te_test_idm.argtypes = [C.c_int, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp, i64]
     L.te_test_powf4_exhaustive.argtypes = [C.c_int, C.c_uint64, vp]
+    L.te_test_fdiv_const_exhaustive.argtypes = [C.c_int, C.c_float, vp]
     L.te_test_philox.argtypes = [C.c_int, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("te_default_config", "te_last_error"):

@@ -719,6 +719,20 @@ extern "C" int te_test_powf4_exhaustive(int device, uint64_t tau, uint64_t out[4
   return 0;
 }
 
+extern "C" int te_test_fdiv_const_exhaustive(int device, float cst, uint64_t out[3]) {
+  if (!out) return fail("te_test_fdiv_const_exhaustive: null argument");
+  CU(cudaSetDevice(device));
+  unsigned long long *d = nullptr;
+  CU(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  CU(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
+  volatile float y = 1.0f / cst;
+  te_fdiv_const_exhaustive_kernel<<<148 * 16, 256>>>(cst, y, d);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
 extern "C" int te_test_philox(int device, const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
   CU(cudaSetDevice(device));
   uint32_t *d = nullptr;

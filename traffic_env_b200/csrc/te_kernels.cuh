@@ -775,6 +775,27 @@ __global__ void te_powf4_exhaustive_kernel(unsigned long long tau, unsigned long
   atomicAdd(&out[0], diff); atomicMax(&out[1], maxd); atomicAdd(&out[2], slow); atomicAdd(&out[3], bad);
 }
 
+// Exhaustive check of the float division by a constant: for EVERY non-negative finite float v, is
+// fma(fma(-c, v*y, v), y, v*y) with y = RN_f32(1/c) equal to RN_f32(v / c)?  out[0] = #mismatches,
+// out[1] = #mismatches whose quotient is a normal float, out[2] = largest v (bits) that mismatches.
+__global__ void te_fdiv_const_exhaustive_kernel(float cst, float y, unsigned long long *out) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long bad = 0, bad_normal = 0, maxv = 0;
+  for (unsigned long long ix = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ix < 0x7f800000ull; ix += stride) {
+    const float v = __uint_as_float((uint32_t)ix);
+    const float ref = __fdiv_rn(v, cst);
+    const float q = __fmul_rn(v, y);
+    const float r = __fmaf_rn(-cst, q, v);
+    const float got = __fmaf_rn(r, y, q);
+    if (__float_as_uint(ref) != __float_as_uint(got)) {
+      bad++;
+      if (__float_as_uint(ref) >= 0x00800000u) bad_normal++;
+      if (ix > maxv) maxv = ix;
+    }
+  }
+  atomicAdd(&out[0], bad); atomicAdd(&out[1], bad_normal); atomicMax(&out[2], maxv);
+}
+
 __global__ void te_test_philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
   uint32_t o[4];
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);
