@@ -39,6 +39,7 @@ constexpr int RING = CAP - 1;      // live ring positions 1..19
 constexpr int YELLOW_TICKS = 6;    // traffic_env.py:21
 constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
 constexpr int WARP_ITEMS = 1280;   // per-warp compaction list: 32 roads * 18 cars = 576 two-byte entries, padded
+constexpr int WARP_BALLOTS = 40;   // per warp: 2 predicates x up to 18 chunks of 32 cars (padded to 20)
 constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
@@ -115,7 +116,7 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 }
 
 struct SmemLayout {
-  int xs, vs, ws, tabs, mbar, tailx, meta, wait, items, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
+  int xs, vs, ws, tabs, mbar, tailx, meta, wait, items, ballots, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
 };
 
 __host__ __device__ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -136,6 +137,7 @@ __host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_en
   L.snap = o; o += (MAX_K + 1) * 8;                    // Philox (draw, skip) before each tick
   L.misc = o; o += 32;
   L.items = o; o += (Rp / GROUP_ROADS) * WARP_ITEMS;
+  L.ballots = o; o += (Rp / GROUP_ROADS) * WARP_BALLOTS * 4;
   L.phase = o; o += align_up(I, 4);
   L.act = o; o += align_up(I, 4);
   L.pdst = o; o += align_up(I, 4);
@@ -200,6 +202,7 @@ struct Smem {
   uint32_t *snap;
   int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks, [6] cars that left the map
   uint8_t *items, *phase, *act, *pdst, *cnt;
+  uint32_t *ballots;
   PowfTables *tabs;
 };
 
@@ -209,7 +212,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) 
   s.tailx = (float *)(base + L.tailx); s.mbar = (unsigned long long *)(base + L.mbar);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
-  s.misc = (int *)(base + L.misc); s.items = base + L.items; s.phase = base + L.phase; s.act = base + L.act;
+  s.misc = (int *)(base + L.misc); s.items = base + L.items; s.ballots = (uint32_t *)(base + L.ballots); s.phase = base + L.phase; s.act = base + L.act;
   s.pdst = base + L.pdst; s.cnt = base + L.cnt; s.tabs = (PowfTables *)(base + L.tabs);
   return s;
 }
@@ -370,6 +373,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   const int dst = is_train ? my_road % p.V : 0;
   const int road_phase = (my_road / p.V) < 2;
   unsigned short *items = reinterpret_cast<unsigned short *>(s.items + warp * WARP_ITEMS);
+  uint32_t *sball = s.ballots + warp * WARP_BALLOTS;
   __syncthreads();
 
   const IdmConst c = p.idm;
@@ -401,7 +405,6 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     const int total = __shfl_sync(FULL, incl, 31);
     for (int k = 0; k < n; k++) items[start + k] = (unsigned short)(lane | (k << 8));  // owning lane, car index
     __syncwarp();
-    int wacc = 0, dacc = 0;
     for (int ch = (total + 31) / 32 - 1; ch >= 0; --ch) {
       const int ci = ch * 32 + lane;
       const bool valid = ci < total;
@@ -438,19 +441,22 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       const uint32_t bw = __ballot_sync(FULL, pw), bd = __ballot_sync(FULL, pdet);
       __syncwarp();  // every lane has read its leader before any lane overwrites a slot (Jacobi update)
       if (valid) { s.xs[o] = xn; s.vs[o] = vn; }
-      // my road's cars sit in lanes [lo, hi) of this chunk
-      const int lo = max(start - ch * 32, 0), hi = min(start + n - ch * 32, 32);
-      if (lo < hi) {
-        const uint32_t mask = (hi == 32 ? FULL : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-        wacc += __popc(bw & mask); dacc += __popc(bd & mask);
-      }
+      if (lane == 0) { sball[ch] = bw; sball[WARP_BALLOTS / 2 + ch] = bd; }  // counted per road after the loop
     }
     __syncwarp();
     int npop = 0;
     const int ld_pre = ld;
     if (n > 0) {
       veh_local += n;
-      if (is_train) { wait += wacc; det = dacc; }   // detected is only rewritten for non-empty roads (:194)
+      if (is_train) {
+        // my cars are items [start, start + n) of the warp's list: at most two chunks (n <= 18)
+        const int c0 = start >> 5, lo = start & 31;
+        const int len0 = min(n, 32 - lo), rem = n - len0;
+        const uint32_t m0 = (len0 == 32 ? FULL : ((1u << len0) - 1u)) << lo, m1 = (1u << rem) - 1u;
+        int wacc = __popc(sball[c0] & m0), dacc = __popc(sball[WARP_BALLOTS / 2 + c0] & m0);
+        if (rem > 0) { wacc += __popc(sball[c0 + 1] & m1); dacc += __popc(sball[WARP_BALLOTS / 2 + c0 + 1] & m1); }
+        wait += wacc; det = dacc;                   // detected is only rewritten for non-empty roads (:194)
+      }
       // advance_finished_cars, traffic_env.py:123: pop while the front car is past the end of the road
       int f = ld;
       while (npop < n) {
