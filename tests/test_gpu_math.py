@@ -135,6 +135,9 @@ def test_idm_adversarial_operands():
     v[3 * k:3 * k + 1000] = 0.0
     v[3 * k + 1000:3 * k + 2000] = np.float32(13.89)      # ratio exactly 1
     v[3 * k + 2000:3 * k + 3000] = np.float32(1e30)       # overflowing power
+    v[3 * k + 3000:3 * k + 4000] = np.float32(3e38)       # v * T overflows: s_star = inf
+    vl[3 * k + 3000:3 * k + 3500] = np.float32(3e38)      # ... with v - vl == 0 (t3 stays finite)
+    xl[3 * k + 3000:3 * k + 3250] = np.inf                # ... behind a free road: inf / inf
     special = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 0.0, -0.0], np.float32)
     idx = rng.randint(4 * k, n, size=30000)
     x[idx[:10000]] = rng.choice(special, 10000)
