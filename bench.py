@@ -231,6 +231,10 @@ def b200_arm(a):
         env.step_device(d_act, d_obs, d_rew, d_done, stream=stream)
         launches[0] += 1
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # nvidia-smi needs a few hundred ms to deliver its first sample; the pre-roll, the warm-up
+                          # and the timed region run the same kernel back to back, so all samples are under load
     for s in range(preroll):
         device_step(s)
     torch.cuda.synchronize()
@@ -242,9 +246,6 @@ def b200_arm(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()   # under load from the warm-up on: the timed region alone can be shorter than one sample
     for s in range(a.warmup):
         device_step(s)
     barrier()
