@@ -132,9 +132,61 @@ def run_wrapped(ref, name, m, n, length, actor_steps, K, n_envs, action_seed=123
     print("%-28s envs=%d steps=%d done_steps=%d" % (name, n_envs, actor_steps, done_out.sum()))
 
 
+def run_random_entry(ref, name, episodes=4, ticks_per_episode=150):
+    """FLAGS.entry == 'random' (traffic_env.py:389-394): reset_entrypoints() re-draws the open sides between
+    episodes while the arrival generator (and its RandomState) carries on.  Recorded: the arrivals the reference
+    actually made (its `rand.choice` results per tick), the entry sets, per-tick digests."""
+    set_flags(ref, entry="random", local_cars_per_sec=0.3)
+    np.random.seed(2)
+    env = rh.make_env(ref, 3, 3, 250, seed=21)
+
+    class Spy(object):
+        def __init__(self, rand):
+            self.rand, self.log = rand, []
+
+        def choice(self, a):
+            r = self.rand.choice(a)
+            self.log.append(int(r))
+            return r
+
+        def __getattr__(self, k):
+            return getattr(self.rand, k)
+    spy = Spy(env.rand)
+    env.rand = spy
+    # NB: the generator created by seed_generator() keeps using the original RandomState object (same stream)
+    digests, dones, entries, actions, per_tick, phases = [], [], [], [], [], []
+    rng = np.random.RandomState(5)
+    for ep in range(episodes):
+        env.reset_entrypoints()
+        entries.append(env.graph.entrypoints.copy())
+        env.reset()
+        phases.append(env.current_phase.copy())
+        for t in range(ticks_per_episode):
+            if t % 10 == 0:
+                a = rng.randint(2, size=9).astype(np.int32)
+            n0 = len(spy.log)
+            obs, rew, done, _ = env.step(a)
+            per_tick.append(spy.log[n0:])
+            xs, vs = rh.live_state(env)
+            digests.append(tick_digest(env.leading, env.lastcar, env.obs, env.waiting, env.passed_dst, rew, done, xs, vs))
+            dones.append(done)
+            actions.append(a.copy())
+    off, roads = pack_schedule(per_tick)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="random_entry", episodes=episodes,
+                        ticks_per_episode=ticks_per_episode, digests=np.asarray(digests, np.uint64),
+                        dones=np.asarray(dones, np.uint8), actions=np.asarray(actions, np.uint8),
+                        init_phases=np.asarray(phases, np.int32), sched_off=off, sched_roads=roads,
+                        entry_sizes=np.asarray([len(e) for e in entries]), entries=np.concatenate(entries))
+    print("%-28s episodes=%d entry sets=%s cars=%d" % (name, episodes, [len(e) for e in entries], len(spy.log)))
+    set_flags(ref)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = rh.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "random_entry":
+        run_random_entry(ref, "entry_random_3x3")
+        return
 
     def fixed(t, env):  # algorithms/fixed.py:6-7 with spacing=3 at K=10
         I = env.graph.intersections

@@ -136,3 +136,85 @@ def test_writes_to_obs_views_reach_the_device(dropin):
     u.elapsed[:] = 3
     u.step(np.ones(9, np.int32))   # no change of phase: elapsed keeps counting from the written value
     assert list(u.current_phase) == [1] * 9 and list(u.elapsed) == [4] * 9
+
+
+def test_full_wrapper_stack_and_launcher(dropin):
+    """traffic_test.make_env's optional layers (Warmup, Localize, Squish, History, UnGSpace) on the B200 env, and
+    the baseline-controller launcher."""
+    gym, GridRoad, FLAGS = dropin
+    from traffic_env_b200.wrappers import make_env
+    np.random.seed(4)
+    env = make_env(seed=1, light_iterations=10, warmup_lights=2, local_weight=3, history=4)
+    obs = env.reset()
+    assert obs.shape == (4, 81) and env.observation_space.shape == [4, 81]
+    o2, r, d, _ = env.step(np.zeros(9))
+    assert o2.shape == (4, 81) and (o2[:3] == obs[1:]).all()       # history slides by one
+    assert r.shape == (9,)
+    # Localize: own reward counted local_weight times
+    base_r = env.unwrapped.rewards.copy()
+    want = np.mean(np.diag(base_r) * 2 + base_r, axis=1) / 3
+    assert np.allclose(r, want)
+    np.random.seed(5)
+    single = make_env(seed=2, light_iterations=10, squish_rewards=True, single_agent=True)
+    single.reset()
+    o, r, d, _ = single.step(5)                                     # Discrete(9) index (UnGSpaceWrapper semantics)
+    assert list(single.unwrapped.current_phase) == [1] * 9          # a one-element action broadcasts, as in the reference
+    assert np.isscalar(r) or np.ndim(r) == 0
+    assert single.action_space.n == 9
+    from traffic_env_b200 import run
+    for trainer in ("fixed", "greedy", "random", "const0", "const1"):
+        mean = run.main(["--trainer", trainer, "--episodes", "2", "--episode_secs", "100"])
+        assert np.isfinite(mean)
+
+
+def test_random_entry_sides(dropin):
+    """FLAGS.entry == 'random' (traffic_env.py:390): the open sides change with reset_entrypoints()."""
+    gym, GridRoad, FLAGS = dropin
+    FLAGS.entry = "random"
+    try:
+        np.random.seed(11)
+        u = new_env(gym, GridRoad, seed=3)
+        seen = set()
+        for _ in range(4):
+            u.reset_entrypoints()
+            u.reset()
+            for _ in range(30):
+                u.step(np.zeros(9))
+            seen.add(tuple(u.graph.entrypoints))
+            counts = u.cars_on_roads()
+            assert counts.sum() >= 0
+        assert len(seen) >= 2
+    finally:
+        FLAGS.entry = "all"
+
+
+def test_random_entry_matches_reference_recording(dropin):
+    """FLAGS.entry == 'random' across four episodes, against a recording of the unmodified reference
+    (tests/golden/entry_random_3x3.npz): the open sides are re-drawn by reset_entrypoints() while the arrival
+    generator carries on - the drop-in must make the same arrivals and reach the same state on every tick."""
+    gym, GridRoad, FLAGS = dropin
+    g = np.load(os.path.join(GOLDEN, "entry_random_3x3.npz"))
+    FLAGS.entry, FLAGS.local_cars_per_sec = "random", 0.3
+    try:
+        np.random.seed(2)
+        u = new_env(gym, GridRoad, seed=21)
+        T = int(g["ticks_per_episode"])
+        eoff = np.concatenate([[0], np.cumsum(g["entry_sizes"])])
+        i = 0
+        for ep in range(int(g["episodes"])):
+            u.reset_entrypoints()
+            assert list(u.graph.entrypoints) == list(g["entries"][eoff[ep]:eoff[ep + 1]])
+            u.reset()
+            assert (u.current_phase == g["init_phases"][ep]).all()
+            for t in range(T):
+                obs, rew, done, _ = u.step(g["actions"][i].astype(np.int32))
+                if t % 10 == 9 or t < 3:
+                    u.sync_counters()
+                    st = u._snapshot()
+                    xs, vs = live_walk(st["leading"][0], st["lastcar"][0], st["x"][0], st["v"][0])
+                    d = tick_digest(st["leading"][0], st["lastcar"][0], obs, u.waiting, u.passed_dst, rew, done, xs, vs)
+                    assert d == g["digests"][i], "episode %d tick %d" % (ep, t)
+                assert done == bool(g["dones"][i])
+                i += 1
+    finally:
+        FLAGS.entry, FLAGS.local_cars_per_sec = "all", 0.12

@@ -92,8 +92,10 @@ class TrafficEnv(gym.Env):
         self._seed = seed
         self._seeded = True
         self._stream = None  # built lazily: FLAGS.cars_per_sec may still change (reset_entrypoints)
+        self._win_snapshot = None
         if getattr(self, "_sim", None) is not None:
             self._sched_end = self._ticks_total  # drop what the old generator had scheduled ahead
+            self._window = []
 
     def reset_entrypoints(self):
         if FLAGS.entry == "random":
@@ -106,8 +108,21 @@ class TrafficEnv(gym.Env):
         self.graph.generate_entrypoints(spec)
         FLAGS.cars_per_sec = FLAGS.local_cars_per_sec * self.graph.m * inv_popcount(spec)
         if getattr(self, "_sim", None) is not None and self._sim_key() != self._key:
-            self._sim.close()
-            self._sim = None  # topology of entries changed: rebuild the device handle lazily
+            # the open sides changed.  The reference keeps its generator (same RandomState, same rate) and simply
+            # draws future cars from the new entry list: rewind the pre-drawn window to the current tick first.
+            consumed = self._ticks_total - self._sched_begin
+            if getattr(self, "_stream", None) is not None:
+                self._stream.restore(self._win_snapshot)
+                self._stream.window(consumed)                      # re-draw what was executed, old entry list
+                self._stream.entrypoints = np.asarray(self.graph.entrypoints)
+            old = self._sim
+            carry = (self._ticks_total, old.get_state(0, 1))
+            old.close()
+            self._sim = None
+            self._device()                                         # new handle: new entry tables
+            self._ticks_total = self._sched_begin = self._sched_end = 0
+            self._sim.set_state(carry[1])
+            self._mirror[:] = self.obs
 
     # ------------------------------------------------------------------ device plumbing
     def _sim_key(self):
@@ -139,7 +154,14 @@ class TrafficEnv(gym.Env):
             self._stream = ArrivalStream(self._seed, self.graph.entrypoints, FLAGS.cars_per_sec, FLAGS.rate,
                                          poisson=bool(FLAGS.poisson))
         # the window must start at the current clock: keep the not-yet-consumed tail of the old window
-        tail = self._window[self._ticks_total - self._sched_begin:] if self._sched_end > self._ticks_total else []
+        consumed = self._ticks_total - self._sched_begin
+        tail = self._window[consumed:] if self._sched_end > self._ticks_total else []
+        # snapshot of the stream at the start of the new window (= at the current tick): rewind, replay what ran
+        if getattr(self, "_win_snapshot", None) is not None and self._window:
+            self._stream.restore(self._win_snapshot)
+            self._stream.window(consumed)
+            tail = []
+        self._win_snapshot = self._stream.snapshot()
         fresh = self._stream.window(max(_WINDOW, ticks) - len(tail))
         self._window = tail + fresh
         self._sched_begin = self._ticks_total
@@ -154,6 +176,12 @@ class TrafficEnv(gym.Env):
         self.rewards[:] = rewards
         self._ticks_total += ticks
         self.steps = np.float32(self.steps + np.float32(ticks))
+
+    def _as_action(self, action):
+        """Truthiness per intersection, with numpy broadcasting like the reference's logical_xor(current_phase, action)
+        (traffic_env.py:229): a one-element action (UnGSpaceWrapper's unravelled index) applies to every light."""
+        a = np.asarray(action).astype(bool)
+        return np.broadcast_to(a.reshape(-1), (self.graph.intersections,)).reshape(1, -1)
 
     def _push_if_dirty(self):
         """`obs` aliases live state in the reference (current_phase, elapsed, detected are views the callers
@@ -185,7 +213,7 @@ class TrafficEnv(gym.Env):
         sim = self._device()
         self._ensure_schedule(1)
         self._push_if_dirty()
-        obs, rew, done = sim.step_raw(np.asarray(action).astype(bool).reshape(1, -1))
+        obs, rew, done = sim.step_raw(self._as_action(action))
         self._pull(obs[0], rew[0], 1)
         return self.obs, self.rewards, bool(done[0]), None
 
@@ -196,7 +224,7 @@ class TrafficEnv(gym.Env):
         self._ensure_schedule(repeat_count)
         self._push_if_dirty()
         t0 = sim.stats()["ticks"]
-        obs, rew, done = sim.step(np.asarray(action).astype(bool).reshape(1, -1), k=repeat_count)
+        obs, rew, done = sim.step(self._as_action(action), k=repeat_count)
         ticks = sim.stats()["ticks"] - t0
         st = sim.get_state(0, 1)
         raw = st["obs"][0]
