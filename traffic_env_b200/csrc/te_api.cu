@@ -66,8 +66,8 @@ struct te_handle {
   int smem_optin;
 };
 
-// One thread per (padded) road.  The register cap follows from the CTA size and the number of CTAs the
-// shared-memory footprint lets an SM hold: 448 threads (10x10 grid) x 2 CTAs -> 72 registers.
+// One thread per (padded) road.  The register cap follows from the CTA size and the number of CTAs an SM should
+// hold (1024 resident threads at 64 registers; 448 threads (10x10 grid) x 2 CTAs, shared-memory bound -> 72).
 typedef void (*step_kernel_t)(const StepParams);
 static step_kernel_t step_kernel_for(int threads, bool validate) {
   if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
@@ -75,10 +75,11 @@ static step_kernel_t step_kernel_for(int threads, bool validate) {
     if (threads <= 512) return te_step_kernel<512, 1, true>;
     return te_step_kernel<1024, 1, true>;
   }
-  if (threads <= 128) return te_step_kernel<128, 4, false>;
-  if (threads <= 256) return te_step_kernel<256, 3, false>;
+  if (threads <= 64) return te_step_kernel<64, 16, false>;   // default 3x3 grid: 2 warps per env, 16 envs per SM
+  if (threads <= 128) return te_step_kernel<128, 8, false>;
+  if (threads <= 256) return te_step_kernel<256, 4, false>;
   if (threads <= 448) return te_step_kernel<448, 2, false>;
-  if (threads <= 512) return te_step_kernel<512, 1, false>;
+  if (threads <= 512) return te_step_kernel<512, 2, false>;
   return te_step_kernel<1024, 1, false>;
 }
 
