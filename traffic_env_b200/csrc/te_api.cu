@@ -66,21 +66,24 @@ struct te_handle {
   int smem_optin;
 };
 
-// One thread per (padded) road.  The register cap follows from the CTA size and the number of CTAs an SM should
-// hold (1024 resident threads at 64 registers; 448 threads (10x10 grid) x 2 CTAs, shared-memory bound -> 72).
+// One thread per (padded) road.  A kernel variant is compiled per row capacity MAXT >= Rp (its shared-memory layout
+// is a compile-time function of MAXT); the register cap follows from the CTA size and the number of CTAs an SM
+// should hold (1024 resident threads at 64 registers; 448 threads (10x10 grid) x 2 CTAs, shared-memory bound -> 72).
 typedef void (*step_kernel_t)(const StepParams);
-static step_kernel_t step_kernel_for(int threads, bool validate) {
+struct StepVariant { step_kernel_t fn; int maxt; };
+static StepVariant step_variant_for(int threads, bool validate) {
   if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
-    if (threads <= 256) return te_step_kernel<256, 2, true>;
-    if (threads <= 512) return te_step_kernel<512, 1, true>;
-    return te_step_kernel<1024, 1, true>;
+    if (threads <= 256) return {te_step_kernel<256, 2, true>, 256};
+    if (threads <= 512) return {te_step_kernel<512, 1, true>, 512};
+    return {te_step_kernel<768, 1, true>, 768};
   }
-  if (threads <= 64) return te_step_kernel<64, 16, false>;   // default 3x3 grid: 2 warps per env, 16 envs per SM
-  if (threads <= 128) return te_step_kernel<128, 8, false>;
-  if (threads <= 256) return te_step_kernel<256, 4, false>;
-  if (threads <= 448) return te_step_kernel<448, 2, false>;
-  if (threads <= 512) return te_step_kernel<512, 2, false>;
-  return te_step_kernel<1024, 1, false>;
+  if (threads <= 64) return {te_step_kernel<64, 16, false>, 64};   // default 3x3 grid: 2 warps per env, 16 envs per SM
+  if (threads <= 128) return {te_step_kernel<128, 8, false>, 128};
+  if (threads <= 256) return {te_step_kernel<256, 4, false>, 256};
+  if (threads <= 448) return {te_step_kernel<448, 2, false>, 448};
+  if (threads <= 512) return {te_step_kernel<512, 2, false>, 512};
+  if (threads <= 768) return {te_step_kernel<768, 1, false>, 768};
+  return {te_step_kernel<1024, 1, false>, 1024};
 }
 
 // The double literals of the IDM update live in constant memory (te_math.cuh: g_mc); one upload per device.
@@ -280,9 +283,11 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
   CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const bool validate = (cfg->flags & TE_VALIDATE) != 0;
-  const SmemLayout L = make_layout(h->Rp, h->I, MAX_K, h->n_entry, validate);
-  if (L.total > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", L.total, h->smem_optin); }
-  CUH(cudaFuncSetAttribute(step_kernel_for(h->Rp, validate), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  const StepVariant sv = step_variant_for(h->Rp, validate);
+  if (h->Rp > sv.maxt) { free_handle(h); return fail("te_create: %d roads exceed the largest%s kernel variant (%d)", h->Rp, validate ? " validate-mode" : "", sv.maxt); }
+  const int smem_max = smem_bytes(sv.maxt, validate, MAX_K, h->n_entry);
+  if (smem_max > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", smem_max, h->smem_optin); }
+  CUH(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
   te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
@@ -399,9 +404,9 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     CU(cudaGetLastError());
   }
   const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
-  const SmemLayout L = make_layout(h->Rp, h->I, K, h->n_entry, validate);
+  const StepVariant sv = step_variant_for(h->Rp, validate);
   CU(cudaEventRecord(h->ev0, st));
-  step_kernel_for(h->Rp, validate)<<<h->cfg.num_envs, h->Rp, L.total, st>>>(p);
+  sv.fn<<<h->cfg.num_envs, h->Rp, smem_bytes(sv.maxt, validate, K, h->n_entry), st>>>(p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
@@ -604,13 +609,14 @@ extern "C" int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
   const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
-  const SmemLayout L = make_layout(h->Rp, h->I, 10, h->n_entry, validate);
-  CU(cudaFuncSetAttribute(te_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  // same dynamic shared-memory footprint as the step kernel, so the same number of CTAs (copies in flight) per SM
+  const int stage_smem = smem_bytes(step_variant_for(h->Rp, validate).maxt, validate, 10, h->n_entry);
+  CU(cudaFuncSetAttribute(te_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_smem));
   StepParams p = h->base;
   p.K = 10;
-  te_stage_kernel<<<h->cfg.num_envs, h->Rp, L.total, h->stream>>>(p, validate);  // warm-up (state is rewritten unchanged)
+  te_stage_kernel<<<h->cfg.num_envs, h->Rp, stage_smem, h->stream>>>(p, validate);  // warm-up (state is rewritten unchanged)
   CU(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < repeats; i++) te_stage_kernel<<<h->cfg.num_envs, h->Rp, L.total, h->stream>>>(p, validate);
+  for (int i = 0; i < repeats; i++) te_stage_kernel<<<h->cfg.num_envs, h->Rp, stage_smem, h->stream>>>(p, validate);
   CU(cudaEventRecord(h->ev1, h->stream));
   CU(cudaEventSynchronize(h->ev1));
   CU(cudaGetLastError());

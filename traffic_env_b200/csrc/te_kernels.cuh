@@ -38,8 +38,7 @@ constexpr int CAP = 20;            // CAPACITY, traffic_env.py:24
 constexpr int RING = CAP - 1;      // live ring positions 1..19
 constexpr int YELLOW_TICKS = 6;    // traffic_env.py:21
 constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
-constexpr int WARP_ITEMS = 1280;   // per-warp compaction list: 32 roads * 18 cars = 576 two-byte entries, padded
-constexpr int WARP_BALLOTS = 40;   // per warp: 2 predicates x up to 18 chunks of 32 cars (padded to 20)
+constexpr int WARP_AREA = 448;     // per-warp tables of the car loop: 32 x (8 B road entry + 4 B counters + 2 B list start)
 constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
@@ -115,35 +114,41 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
   return (uint32_t)leading | ((uint32_t)lastcar << 8) | ((uint32_t)detected << 16);
 }
 
+// Shared-memory layout of one CTA.  Every offset is a compile-time function of the kernel variant's row capacity
+// MAXT (>= Rp) so that the tick loop addresses shared memory with immediates; only the arrival-count table at the
+// very end has a run-time size (K * n_entry bytes).
 struct SmemLayout {
-  int xs, vs, ws, tabs, mbar, tailx, meta, wait, items, ballots, elapsed, ovf, snap, misc, phase, act, pdst, cnt, total;
+  int xs, vs, ws, tabs, mbar, tailx, meta, wait, elapsed, ovf, snap, misc, warp, phase, act, pdst, cnt;
 };
 
-__host__ __device__ inline int align_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ constexpr int align_up(int a, int b) { return (a + b - 1) / b * b; }
 
-__host__ __device__ inline SmemLayout make_layout(int Rp, int I, int K, int n_entry, bool validate) {
-  SmemLayout L;
+__host__ __device__ constexpr SmemLayout make_layout(int maxt, bool validate) {
+  SmemLayout L = {};
+  const int icap = align_up(maxt / 4, 4);               // 4 I = r < R <= Rp <= maxt
   int o = 0;
-  L.xs = o; o += Rp * CAP * 4;
-  L.vs = o; o += Rp * CAP * 4;
-  L.ws = o; o += validate ? Rp * CAP * 4 : 0;
-  L.tabs = o; o += (int)sizeof(PowfTables);            // 512 B, 8-aligned
+  L.xs = o; o += maxt * CAP * 4;
+  L.vs = o; o += maxt * CAP * 4;
+  L.ws = o; o += validate ? maxt * CAP * 4 : 0;
+  L.tabs = o; o += (int)sizeof(PowfTables);             // 512 B, 8-aligned
   L.mbar = o; o += 8;
-  L.tailx = o; o += Rp * 4;
-  L.meta = o; o += Rp * 4;
-  L.wait = o; o += Rp * 4;
-  L.elapsed = o; o += align_up(I, 4) * 4;
-  L.ovf = o; o += align_up(I, 4) * 4;
-  L.snap = o; o += (MAX_K + 1) * 8;                    // Philox (draw, skip) before each tick
+  L.tailx = o; o += maxt * 4;
+  L.meta = o; o += maxt * 4;
+  L.wait = o; o += maxt * 4;
+  L.elapsed = o; o += icap * 4;
+  L.ovf = o; o += icap * 4;
+  L.snap = o; o += (MAX_K + 1) * 8;                     // Philox (draw, skip) before each tick
   L.misc = o; o += 32;
-  L.items = o; o += (Rp / GROUP_ROADS) * WARP_ITEMS;
-  L.ballots = o; o += (Rp / GROUP_ROADS) * WARP_BALLOTS * 4;
-  L.phase = o; o += align_up(I, 4);
-  L.act = o; o += align_up(I, 4);
-  L.pdst = o; o += align_up(I, 4);
-  L.cnt = o; o += align_up(K * (n_entry > 0 ? n_entry : 1), 16);
-  L.total = align_up(o, 16);
+  L.warp = o; o += (maxt / GROUP_ROADS) * WARP_AREA;
+  L.phase = o; o += icap;
+  L.act = o; o += icap;
+  L.pdst = o; o += icap;
+  L.cnt = align_up(o, 16);
   return L;
+}
+
+__host__ __device__ constexpr int smem_bytes(int maxt, bool validate, int K, int n_entry) {
+  return make_layout(maxt, validate).cnt + align_up(K * (n_entry > 0 ? n_entry : 1), 16);
 }
 
 // ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier: the env's ring planes are contiguous in HBM, so
@@ -201,8 +206,7 @@ struct Smem {
   unsigned long long *mbar;
   uint32_t *snap;
   int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks, [6] cars that left the map
-  uint8_t *items, *phase, *act, *pdst, *cnt;
-  uint32_t *ballots;
+  uint8_t *warp, *phase, *act, *pdst, *cnt;
   PowfTables *tabs;
 };
 
@@ -212,7 +216,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) 
   s.tailx = (float *)(base + L.tailx); s.mbar = (unsigned long long *)(base + L.mbar);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
-  s.misc = (int *)(base + L.misc); s.items = base + L.items; s.ballots = (uint32_t *)(base + L.ballots); s.phase = base + L.phase; s.act = base + L.act;
+  s.misc = (int *)(base + L.misc); s.warp = base + L.warp; s.phase = base + L.phase; s.act = base + L.act;
   s.pdst = base + L.pdst; s.cnt = base + L.cnt; s.tabs = (PowfTables *)(base + L.tabs);
   return s;
 }
@@ -240,7 +244,7 @@ __device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int 
 template <int MAXT, int MINB, bool VALIDATE>
 __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry, VALIDATE);
+  constexpr SmemLayout L = make_layout(MAXT, VALIDATE);
   const Smem s = carve(smem_raw, L);
   const int env = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,8 +341,8 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   const int nwarps = blockDim.x >> 5;            // blockDim.x == Rp
   int my_road;
   {
-    int *hist = reinterpret_cast<int *>(s.items);            // [0..19] counts, [20..39] tickets (items list is idle here)
-    short *owner = reinterpret_cast<short *>(s.items + 160);
+    int *hist = s.wait;                                      // [0..19] counts, [20..39] tickets (idle until the epilogue)
+    short *owner = reinterpret_cast<short *>(s.meta);        // idle until the tick loop
     for (int i = tid; i < 40; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const uint32_t w0 = __float_as_uint(s.xs[tid * CAP]);
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     owner[w * 32 + row] = (short)tid;
     __syncthreads();
     my_road = owner[tid];
-    __syncthreads();                                         // the items region is reused by the tick loop
+    __syncthreads();                                         // the scratch regions are reused below
   }
   // ---- lane = road: ring indices, counters and topology of my road live in registers
   const bool is_road = my_road < p.R, is_train = my_road < p.r;
@@ -371,9 +375,21 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   }
   const int nxt = p.nexts[my_road], upr = p.up[my_road], ei = p.entry_idx[my_road];
   const int dst = is_train ? my_road % p.V : 0;
-  const int road_phase = (my_road / p.V) < 2;
-  unsigned short *items = reinterpret_cast<unsigned short *>(s.items + warp * WARP_ITEMS);
-  uint32_t *sball = s.ballots + warp * WARP_BALLOTS;
+  // update_lights (traffic_env.py:81-94) in closed form: within one launch the action is constant, so the approach
+  // is blocked (red or yellow) at tick t  <=>  t < ylim.  learn_switch with a set action toggles every tick, which
+  // keeps elapsed at 0 (always yellow); otherwise phase_t is constant and elapsed_t = elapsed_0 + t.
+  int ylim = 0;
+  if (is_train) {
+    const bool ls_act = learn_switch && s.act[dst];
+    const int road_phase = (my_road / p.V) < 2;
+    const int el0 = s.elapsed[dst];
+    ylim = (ls_act || road_phase == (int)s.phase[dst]) ? 0x7fffffff : YELLOW_TICKS - el0;
+  }
+  // per-warp tables of the car loop (rebuilt every tick)
+  uint2 *rt = reinterpret_cast<uint2 *>(s.warp + warp * WARP_AREA);      // non-empty roads of the warp, in lane order
+  unsigned int *wcnt = reinterpret_cast<unsigned int *>(rt + 32);        // waiting | detected << 16 per listed road
+  unsigned short *wst = reinterpret_cast<unsigned short *>(wcnt + 32);   // first list position of each listed road
+  const unsigned lt_mask = (1u << lane) - 1u;
   __syncthreads();
 
   const IdmConst c = p.idm;
@@ -389,73 +405,95 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         if (!ring_push(xr, vr, wr, ld, lc, c.x_new, c.v_new, steps0 + (float)t, c)) dropped++;  // car[wi] = tick, :279
       }
     }
-    if (is_train) {  // update_lights, traffic_env.py:81-94
-      const bool ls_act = learn_switch && s.act[dst];
-      const int ph_t = s.phase[dst] ^ (ls_act ? (t & 1) : 0);
-      const int el_t = ls_act ? 0 : s.elapsed[dst] + t;
-      if (road_phase == ph_t || el_t < YELLOW_TICKS) leadx = p.length;
+    if (is_train) {  // update_lights
+      if (t < ylim) leadx = p.length;
       else leadx = nxt >= 0 ? __fadd_rn(s.tailx[nxt], p.length) : INF;
     }
     const int n = ring_count(ld, lc);
-    // compaction: exclusive prefix sum of the per-road car counts over the warp
+    // The warp's live cars, road after road in ring order, form one list of `total` cars; lane l simulates the
+    // q = ceil(total / 32) consecutive cars [l q, l q + q).  A car's leader is the list entry before it (or the
+    // road's virtual leader), so a lane keeps the leader's PRE-update (x, v) in registers from its previous
+    // iteration - the Jacobi update of sim (:50-62) / move_cars (:187-212) - and only the first car of a run reads
+    // its leader from shared memory, before any lane has written (the __syncwarp below).
     int incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
     const int start = incl - n;
     const int total = __shfl_sync(FULL, incl, 31);
-    for (int k = 0; k < n; k++) items[start + k] = (unsigned short)(lane | (k << 8));  // owning lane, car index
-    __syncwarp();
-    for (int ch = (total + 31) / 32 - 1; ch >= 0; --ch) {
-      const int ci = ch * 32 + lane;
-      const bool valid = ci < total;
-      const int it = valid ? items[ci] : 0;
-      const int j = it & 31, k = it >> 8;                  // owning road lane, k-th car from the front of its road
-      const int ldj = __shfl_sync(FULL, ld, j), lcj = __shfl_sync(FULL, lc, j);
-      const float lxj = __shfl_sync(FULL, leadx, j);
-      float xn = 0.f, vn = 0.f;
-      bool pw = false, pdet = false;
-      int o = 0, slot = 1;
-      const int rbase = __shfl_sync(FULL, my_road, j) * CAP;
-      if (valid) {
-        const int tt = ldj + k;
-        slot = tt < RING ? tt + 1 : tt - (RING - 1);         // ((ld + k) mod 19) + 1
-        o = rbase + slot;
-        xn = s.xs[o]; vn = s.vs[o];
-      }
-      // the car ahead is the previous item of the list: the lane below me, or (lane 0) one shared-memory read
-      float xl = __shfl_up_sync(FULL, xn, 1), vl = __shfl_up_sync(FULL, vn, 1), ll = c.len;
-      // lane 0's predecessor sits in the next lower chunk: one predicated shared-memory read instead of the shuffle
-      const int lo0 = rbase + (slot == 1 ? RING : slot - 1);
-      const bool from_smem = valid && lane == 0 && k > 0;
-      if (from_smem) { xl = s.xs[lo0]; vl = s.vs[lo0]; }
-      if (k == 0) { xl = lxj; vl = 0.f; ll = 0.f; }          // virtual leader: v = 0, l = 0
-      if (valid) {
-        idm_update(c, s.tabs, xl, vl, ll, xn, vn);
-        // wrapped ring, low segment: the reference tests x, not v (traffic_env.py:210)
-        const bool lowseg = ldj > lcj && slot <= lcj;
-        // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
-        // float w: (double)w < 0.2  <=>  w < 0.2f.  Same for the detector threshold with det_thr_f (see StepParams).
-        pw = (lowseg ? xn : vn) < 0.2f;
-        pdet = xn > p.det_thr_f;
-      }
-      const uint32_t bw = __ballot_sync(FULL, pw), bd = __ballot_sync(FULL, pdet);
-      __syncwarp();  // every lane has read its leader before any lane overwrites a slot (Jacobi update)
-      if (valid) { s.xs[o] = xn; s.vs[o] = vn; }
-      if (lane == 0) { sball[ch] = bw; sball[WARP_BALLOTS / 2 + ch] = bd; }  // counted per road after the loop
+    const unsigned mne = __ballot_sync(FULL, n > 0);
+    const int nroads = __popc(mne);
+    const int cidx = n > 0 ? __popc(mne & lt_mask) : nroads + __popc(~mne & lt_mask);
+    wst[cidx] = n > 0 ? (unsigned short)start : (unsigned short)0xffff;
+    if (n > 0) {
+      rt[cidx] = make_uint2((uint32_t)my_road | ((uint32_t)ld << 10) | ((uint32_t)n << 15), __float_as_uint(leadx));
+      wcnt[cidx] = 0u;
     }
     __syncwarp();
+    if (total > 0) {
+      const int q = (total + 31) >> 5;
+      const int target = lane * q;
+      bool have = target < total;
+      int j = 0, rem = 0, slot = 1, obase = 0, ldj = 0;
+      bool first = true;
+      float lxj = 0.f, px = 0.f, pv = 0.f;
+      if (have) {
+        int lo = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) if ((int)wst[lo + st] <= target) lo += st;
+        j = lo;
+        const int k = target - (int)wst[lo];
+        const uint2 e = rt[j];
+        obase = (int)(e.x & 1023u) * CAP; ldj = (int)((e.x >> 10) & 31u); rem = (int)((e.x >> 15) & 31u) - k;
+        lxj = __uint_as_float(e.y);
+        const int tt = ldj + k;
+        slot = tt < RING ? tt + 1 : tt - (RING - 1);           // ((ld + k) mod 19) + 1
+        first = k == 0;
+        if (!first) { const int ps = obase + (slot == 1 ? RING : slot - 1); px = s.xs[ps]; pv = s.vs[ps]; }
+      }
+      __syncwarp();  // every run has read the leader of its first car before any lane overwrites a slot
+      unsigned int acc = 0u;
+      for (int i = 0; i < q; i++) {
+        if (have) {
+          const int o = obase + slot;
+          float xn = s.xs[o], vn = s.vs[o];
+          // virtual leader: v = 0, l = 0
+          const float xl = first ? lxj : px, vl = first ? 0.f : pv, ll = first ? 0.f : c.len;
+          px = xn; pv = vn;
+          idm_update(c, s.tabs, xl, vl, ll, xn, vn);
+          s.xs[o] = xn; s.vs[o] = vn;
+          // wrapped ring, low segment (slot < leading): the reference tests x, not v (traffic_env.py:210).
+          // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
+          // float w: (double)w < 0.2  <=>  w < 0.2f.  Same for the detector threshold with det_thr_f (see StepParams).
+          const bool pw = ((slot < ldj) ? xn : vn) < 0.2f;
+          const bool pdet = xn > p.det_thr_f;
+          acc += (pw ? 1u : 0u) + (pdet ? 0x10000u : 0u);
+          first = false;
+          slot = slot == RING ? 1 : slot + 1;
+          if (--rem == 0) {  // the road is done: hand its counts to the road lane, move on to the next listed road
+            atomicAdd(&wcnt[j], acc);
+            acc = 0u;
+            j++;
+            have = j < nroads;
+            if (have) {
+              const uint2 e = rt[j];
+              obase = (int)(e.x & 1023u) * CAP; ldj = (int)((e.x >> 10) & 31u); rem = (int)((e.x >> 15) & 31u);
+              lxj = __uint_as_float(e.y);
+              slot = ldj == RING ? 1 : ldj + 1;
+              first = true;
+            }
+          }
+        }
+      }
+      if (acc) atomicAdd(&wcnt[j], acc);  // counts of a road that continues on the next lane
+      __syncwarp();
+    }
     int npop = 0;
     const int ld_pre = ld;
     if (n > 0) {
       veh_local += n;
       if (is_train) {
-        // my cars are items [start, start + n) of the warp's list: at most two chunks (n <= 18)
-        const int c0 = start >> 5, lo = start & 31;
-        const int len0 = min(n, 32 - lo), rem = n - len0;
-        const uint32_t m0 = (len0 == 32 ? FULL : ((1u << len0) - 1u)) << lo, m1 = (1u << rem) - 1u;
-        int wacc = __popc(sball[c0] & m0), dacc = __popc(sball[WARP_BALLOTS / 2 + c0] & m0);
-        if (rem > 0) { wacc += __popc(sball[c0 + 1] & m1); dacc += __popc(sball[WARP_BALLOTS / 2 + c0 + 1] & m1); }
-        wait += wacc; det = dacc;                   // detected is only rewritten for non-empty roads (:194)
+        const unsigned int cw = wcnt[cidx];
+        wait += (int)(cw & 0xffffu); det = (int)(cw >> 16);  // detected is only rewritten for non-empty roads (:194)
       }
       // advance_finished_cars, traffic_env.py:123: pop while the front car is past the end of the road
       int f = ld;
@@ -620,23 +658,24 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
 // Measures the HBM bandwidth the load/flush phases of te_step_kernel run at.
 __global__ void te_stage_kernel(const StepParams p, int validate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SmemLayout L = make_layout(p.Rp, p.I, p.K, p.n_entry, validate != 0);
-  const Smem s = carve(smem_raw, L);
+  (void)validate;
   const int env = blockIdx.x;
   const uint32_t plane_bytes = (uint32_t)p.Rp * CAP * 4;
+  float *xs = reinterpret_cast<float *>(smem_raw), *vs = reinterpret_cast<float *>(smem_raw + plane_bytes);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + 2 * plane_bytes);
   if (threadIdx.x == 0) {
-    mbar_init(s.mbar, 1);
+    mbar_init(mbar, 1);
     fence_proxy_async();
-    mbar_expect_tx(s.mbar, plane_bytes * 2u);
-    bulk_load(s.xs, p.x + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
-    bulk_load(s.vs, p.v + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+    mbar_expect_tx(mbar, plane_bytes * 2u);
+    bulk_load(xs, p.x + (size_t)env * p.Rp * CAP, plane_bytes, mbar);
+    bulk_load(vs, p.v + (size_t)env * p.Rp * CAP, plane_bytes, mbar);
   }
   __syncthreads();
-  mbar_wait(s.mbar, 0);
+  mbar_wait(mbar, 0);
   __syncthreads();
   if (threadIdx.x == 0) {
-    bulk_store(p.x + (size_t)env * p.Rp * CAP, s.xs, plane_bytes);
-    bulk_store(p.v + (size_t)env * p.Rp * CAP, s.vs, plane_bytes);
+    bulk_store(p.x + (size_t)env * p.Rp * CAP, xs, plane_bytes);
+    bulk_store(p.v + (size_t)env * p.Rp * CAP, vs, plane_bytes);
     bulk_commit_wait();
   }
 }
