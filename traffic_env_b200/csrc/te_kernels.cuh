@@ -38,7 +38,7 @@ constexpr int CAP = 20;            // CAPACITY, traffic_env.py:24
 constexpr int RING = CAP - 1;      // live ring positions 1..19
 constexpr int YELLOW_TICKS = 6;    // traffic_env.py:21
 constexpr int GROUP_ROADS = 32;    // one road per lane of the owning warp
-constexpr int WARP_AREA = 448;     // per-warp tables of the car loop: 32 x (8 B road entry + 4 B counters + 2 B list start)
+constexpr int WARP_AREA = 704;     // per-warp tables of the car loop: 32 x (16 B road entry + 4 B counters + 2 B list start)
 constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
@@ -179,6 +179,33 @@ __device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src,
 __device__ __forceinline__ void bulk_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Explicit shared-window accesses for the car loop: 32-bit shared addresses kept in registers (no generic-pointer
+// arithmetic inside the loop), plane offsets as immediates.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32_off(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ void sts_f32_off(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_shared(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ int ring_wrap(int a) { return a >= CAP ? 1 : a; }
@@ -386,9 +413,13 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     ylim = (ls_act || road_phase == (int)s.phase[dst]) ? 0x7fffffff : YELLOW_TICKS - el0;
   }
   // per-warp tables of the car loop (rebuilt every tick)
-  uint2 *rt = reinterpret_cast<uint2 *>(s.warp + warp * WARP_AREA);      // non-empty roads of the warp, in lane order
+  uint4 *rt = reinterpret_cast<uint4 *>(s.warp + warp * WARP_AREA);      // non-empty roads of the warp, in lane order:
+                                                                         // shared addresses of x[leading], x[lastcar], x[19]; leader x
   unsigned int *wcnt = reinterpret_cast<unsigned int *>(rt + 32);        // waiting | detected << 16 per listed road
   unsigned short *wst = reinterpret_cast<unsigned short *>(wcnt + 32);   // first list position of each listed road
+  const uint32_t rt_a = smem_u32(rt), wcnt_a = smem_u32(wcnt);
+  const uint32_t xrow_a = smem_u32(xr);                                  // shared address of x[my_road][0]
+  constexpr int VOFF = L.vs - L.xs;                                      // v plane relative to the x plane
   const unsigned lt_mask = (1u << lane) - 1u;
   __syncthreads();
 
@@ -425,7 +456,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     const int cidx = n > 0 ? __popc(mne & lt_mask) : nroads + __popc(~mne & lt_mask);
     wst[cidx] = n > 0 ? (unsigned short)start : (unsigned short)0xffff;
     if (n > 0) {
-      rt[cidx] = make_uint2((uint32_t)my_road | ((uint32_t)ld << 10) | ((uint32_t)n << 15), __float_as_uint(leadx));
+      rt[cidx] = make_uint4(xrow_a + 4u * ld, xrow_a + 4u * lc, xrow_a + 4u * RING, __float_as_uint(leadx));
       wcnt[cidx] = 0u;
     }
     __syncwarp();
@@ -433,58 +464,61 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       const int q = (total + 31) >> 5;
       const int target = lane * q;
       bool have = target < total;
-      int j = 0, rem = 0, slot = 1, obase = 0, ldj = 0;
+      // run state: address of my car's x slot; x[leading], x[lastcar], x[19] of its road; table cursors
+      uint32_t addr = 0, ldaddr = 0, lcaddr = 0, endaddr = 0, jaddr = rt_a, caddr = wcnt_a;
+      const uint32_t jend = rt_a + 16u * nroads;
       bool first = true;
       float lxj = 0.f, px = 0.f, pv = 0.f;
       if (have) {
         int lo = 0;
 #pragma unroll
         for (int st = 16; st > 0; st >>= 1) if ((int)wst[lo + st] <= target) lo += st;
-        j = lo;
-        const int k = target - (int)wst[lo];
-        const uint2 e = rt[j];
-        obase = (int)(e.x & 1023u) * CAP; ldj = (int)((e.x >> 10) & 31u); rem = (int)((e.x >> 15) & 31u) - k;
-        lxj = __uint_as_float(e.y);
-        const int tt = ldj + k;
-        slot = tt < RING ? tt + 1 : tt - (RING - 1);           // ((ld + k) mod 19) + 1
+        const int k = target - (int)wst[lo];                   // my first car is the k-th from the front of road `lo`
+        jaddr = rt_a + 16u * lo; caddr = wcnt_a + 4u * lo;
+        const uint4 e = rt[lo];
+        ldaddr = e.x; lcaddr = e.y; endaddr = e.z; lxj = __uint_as_float(e.w);
+        addr = ldaddr + 4u * (k + 1);
+        if (addr > endaddr) addr -= 4u * RING;                 // ring position ((leading + k) mod 19) + 1
         first = k == 0;
-        if (!first) { const int ps = obase + (slot == 1 ? RING : slot - 1); px = s.xs[ps]; pv = s.vs[ps]; }
+        if (!first) {
+          const uint32_t pa = (addr == endaddr - 4u * (RING - 1)) ? endaddr : addr - 4u;  // slot 1 follows slot 19
+          px = lds_f32(pa); pv = lds_f32_off<VOFF>(pa);
+        }
       }
       __syncwarp();  // every run has read the leader of its first car before any lane overwrites a slot
       unsigned int acc = 0u;
       for (int i = 0; i < q; i++) {
         if (have) {
-          const int o = obase + slot;
-          float xn = s.xs[o], vn = s.vs[o];
+          float xn = lds_f32(addr), vn = lds_f32_off<VOFF>(addr);
           // virtual leader: v = 0, l = 0
           const float xl = first ? lxj : px, vl = first ? 0.f : pv, ll = first ? 0.f : c.len;
           px = xn; pv = vn;
           idm_update(c, s.tabs, xl, vl, ll, xn, vn);
-          s.xs[o] = xn; s.vs[o] = vn;
+          sts_f32(addr, xn); sts_f32_off<VOFF>(addr, vn);
           // wrapped ring, low segment (slot < leading): the reference tests x, not v (traffic_env.py:210).
           // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
           // float w: (double)w < 0.2  <=>  w < 0.2f.  Same for the detector threshold with det_thr_f (see StepParams).
-          const bool pw = ((slot < ldj) ? xn : vn) < 0.2f;
+          const bool pw = ((addr < ldaddr) ? xn : vn) < 0.2f;
           const bool pdet = xn > p.det_thr_f;
           acc += (pw ? 1u : 0u) + (pdet ? 0x10000u : 0u);
           first = false;
-          slot = slot == RING ? 1 : slot + 1;
-          if (--rem == 0) {  // the road is done: hand its counts to the road lane, move on to the next listed road
-            atomicAdd(&wcnt[j], acc);
+          const bool road_done = addr == lcaddr;
+          addr = (addr == endaddr) ? addr - 4u * (RING - 1) : addr + 4u;
+          if (road_done) {  // hand the road's counts to its road lane, move on to the next listed road
+            red_add_shared(caddr, acc);
             acc = 0u;
-            j++;
-            have = j < nroads;
+            jaddr += 16u; caddr += 4u;
+            have = jaddr < jend;
             if (have) {
-              const uint2 e = rt[j];
-              obase = (int)(e.x & 1023u) * CAP; ldj = (int)((e.x >> 10) & 31u); rem = (int)((e.x >> 15) & 31u);
-              lxj = __uint_as_float(e.y);
-              slot = ldj == RING ? 1 : ldj + 1;
+              const uint4 e = lds_v4(jaddr);
+              ldaddr = e.x; lcaddr = e.y; endaddr = e.z; lxj = __uint_as_float(e.w);
+              addr = (ldaddr == endaddr) ? ldaddr - 4u * (RING - 1) : ldaddr + 4u;
               first = true;
             }
           }
         }
       }
-      if (acc) atomicAdd(&wcnt[j], acc);  // counts of a road that continues on the next lane
+      if (acc) red_add_shared(caddr, acc);  // counts of a road that continues on the next lane
       __syncwarp();
     }
     int npop = 0;
