@@ -271,6 +271,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.idm.v0_d = (double)a[5]; p.idm.rcp_v0 = 1.0 / (double)a[5];
   p.idm.s0_d = (double)a[8]; p.idm.a_d = (double)a[3]; p.idm.rate_d = (double)cfg->rate; p.idm.delta_d = (double)a[4];
   p.idm.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
+  p.idm.half_rate_d = 0.5 * (double)cfg->rate; p.idm.s0_z = (float)(0.0 + (double)a[8]);
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
@@ -670,6 +671,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
   c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
   c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
+  c.half_rate_d = 0.5 * (double)rate; c.s0_z = (float)(0.0 + (double)a[8]);
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
@@ -693,6 +695,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
   c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
   c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
+  c.half_rate_d = 0.5 * (double)rate; c.s0_z = (float)(0.0 + (double)a[8]);
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM

@@ -463,58 +463,49 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (total > 0) {
       const int q = (total + 31) >> 5;
       const int target = lane * q;
-      bool have = target < total;
-      // run state: address of my car's x slot; x[leading], x[lastcar], x[19] of its road; table cursors
+      const int cnt = min(q, total - target);                  // cars of my run (<= 0: none)
+      // run state: address of my car's x slot; x[leading], x[lastcar], x[19] of its road; table cursors;
+      // (px, pv, pl) = pre-update x, v and length of the car ahead (virtual leader: v = 0, l = 0)
       uint32_t addr = 0, ldaddr = 0, lcaddr = 0, endaddr = 0, jaddr = rt_a, caddr = wcnt_a;
-      const uint32_t jend = rt_a + 16u * nroads;
-      bool first = true;
-      float lxj = 0.f, px = 0.f, pv = 0.f;
-      if (have) {
+      float px = 0.f, pv = 0.f, pl = 0.f;
+      if (cnt > 0) {
         int lo = 0;
 #pragma unroll
         for (int st = 16; st > 0; st >>= 1) if ((int)wst[lo + st] <= target) lo += st;
         const int k = target - (int)wst[lo];                   // my first car is the k-th from the front of road `lo`
         jaddr = rt_a + 16u * lo; caddr = wcnt_a + 4u * lo;
         const uint4 e = rt[lo];
-        ldaddr = e.x; lcaddr = e.y; endaddr = e.z; lxj = __uint_as_float(e.w);
+        ldaddr = e.x; lcaddr = e.y; endaddr = e.z; px = __uint_as_float(e.w);
         addr = ldaddr + 4u * (k + 1);
         if (addr > endaddr) addr -= 4u * RING;                 // ring position ((leading + k) mod 19) + 1
-        first = k == 0;
-        if (!first) {
+        if (k != 0) {
           const uint32_t pa = (addr == endaddr - 4u * (RING - 1)) ? endaddr : addr - 4u;  // slot 1 follows slot 19
-          px = lds_f32(pa); pv = lds_f32_off<VOFF>(pa);
+          px = lds_f32(pa); pv = lds_f32_off<VOFF>(pa); pl = c.len;
         }
       }
       __syncwarp();  // every run has read the leader of its first car before any lane overwrites a slot
       unsigned int acc = 0u;
       for (int i = 0; i < q; i++) {
-        if (have) {
+        if (i < cnt) {
           float xn = lds_f32(addr), vn = lds_f32_off<VOFF>(addr);
-          // virtual leader: v = 0, l = 0
-          const float xl = first ? lxj : px, vl = first ? 0.f : pv, ll = first ? 0.f : c.len;
-          px = xn; pv = vn;
+          const float xl = px, vl = pv, ll = pl;
+          px = xn; pv = vn; pl = c.len;
           idm_update(c, s.tabs, xl, vl, ll, xn, vn);
           sts_f32(addr, xn); sts_f32_off<VOFF>(addr, vn);
           // wrapped ring, low segment (slot < leading): the reference tests x, not v (traffic_env.py:210).
           // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
           // float w: (double)w < 0.2  <=>  w < 0.2f.  Same for the detector threshold with det_thr_f (see StepParams).
-          const bool pw = ((addr < ldaddr) ? xn : vn) < 0.2f;
-          const bool pdet = xn > p.det_thr_f;
-          acc += (pw ? 1u : 0u) + (pdet ? 0x10000u : 0u);
-          first = false;
+          if (((addr < ldaddr) ? xn : vn) < 0.2f) acc += 1u;
+          if (xn > p.det_thr_f) acc += 0x10000u;
           const bool road_done = addr == lcaddr;
           addr = (addr == endaddr) ? addr - 4u * (RING - 1) : addr + 4u;
           if (road_done) {  // hand the road's counts to its road lane, move on to the next listed road
             red_add_shared(caddr, acc);
             acc = 0u;
             jaddr += 16u; caddr += 4u;
-            have = jaddr < jend;
-            if (have) {
-              const uint4 e = lds_v4(jaddr);
-              ldaddr = e.x; lcaddr = e.y; endaddr = e.z; lxj = __uint_as_float(e.w);
-              addr = (ldaddr == endaddr) ? ldaddr - 4u * (RING - 1) : ldaddr + 4u;
-              first = true;
-            }
+            const uint4 e = lds_v4(jaddr);  // (past the last listed road: a stale entry that is never used, cnt ends the run)
+            ldaddr = e.x; lcaddr = e.y; endaddr = e.z; px = __uint_as_float(e.w); pv = 0.f; pl = 0.f;
+            addr = (ldaddr == endaddr) ? ldaddr - 4u * (RING - 1) : ldaddr + 4u;
           }
         }
       }
@@ -850,6 +841,9 @@ __global__ void te_powf4_exhaustive_kernel(unsigned long long tau, unsigned long
     const bool same = __float_as_uint(fast) == __float_as_uint(ref);
     if (!same) { diff++; if (acc) bad++; if (dist > maxd && dist != 0xffffffffu) maxd = dist; }
     if (!acc) slow++;
+    // the step kernel's form of the filter (powf4_fast) must never accept an input whose shortcut differs
+    float fast2;
+    if (powf4_fast(r, fast2) && __float_as_uint(fast2) != __float_as_uint(ref)) bad++;
   }
   atomicAdd(&out[0], diff); atomicMax(&out[1], maxd); atomicAdd(&out[2], slow); atomicAdd(&out[3], bad);
 }
