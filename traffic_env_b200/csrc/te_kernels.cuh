@@ -72,6 +72,7 @@ struct TripRecord {
 struct StepParams {
   int V, r, R, Rp, I, n_entry, G;
   int num_envs;
+  int env0;               // first env of this launch (te_step with host buffers launches the batch in slices)
   float length;
   double det_thr;         // (double)length - 10.0  (traffic_env.py:201: float32 - int64 types as float64)
   float det_thr_f;        // largest float <= det_thr: for every float x, (double)x > det_thr  <=>  x > det_thr_f
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr SmemLayout L = make_layout(MAXT, VALIDATE);
   const Smem s = carve(smem_raw, L);
-  const int env = blockIdx.x;
+  const int env = p.env0 + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned FULL = 0xffffffffu;
   const float INF = __int_as_float(0x7f800000);
