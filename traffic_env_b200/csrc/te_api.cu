@@ -92,6 +92,23 @@ static cudaError_t upload_math_consts() {
   return cudaMemcpyToSymbol(g_mc, &m, sizeof(m));
 }
 
+// IdmConst from the archetype and the tick length (one place: te_create and the test hooks)
+static bool is_pow2_f(float f) {
+  int e = 0;
+  return f > 0.f && std::isfinite(f) && frexpf(f, &e) == 0.5f && e >= -19 && e <= 21;   // 2^-20 .. 2^20
+}
+static void fill_idm(IdmConst &c, const float *a, float rate) {
+  c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
+  { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
+  c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
+  c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
+  c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
+  c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
+  c.half_rate_d = 0.5 * (double)rate; c.s0_z = (float)(0.0 + (double)a[8]);
+  c.T_d = (double)a[7];
+  c.pow2 = is_pow2_f(a[7]) && is_pow2_f(rate) && !getenv("TE_NO_POW2_SHORTCUT");
+}
+
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
 
 extern "C" void te_default_config(te_config *c) {
@@ -269,15 +286,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   }
   p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
   p.gamma = cfg->gamma;
-  const float *a = cfg->archetype;
-  p.idm.rate = cfg->rate; p.idm.x_new = a[0]; p.idm.v_new = a[1]; p.idm.len = a[2]; p.idm.a = a[3];
-  p.idm.delta = a[4]; p.idm.v0 = a[5]; p.idm.T = a[7]; p.idm.s0 = a[8];
-  { volatile float ab = a[3] * a[6]; p.idm.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }  // traffic_env.py:54
-  p.idm.rcp_two_sqrt_ab = 1.0 / p.idm.two_sqrt_ab;
-  p.idm.v0_d = (double)a[5]; p.idm.rcp_v0 = 1.0 / (double)a[5];
-  p.idm.s0_d = (double)a[8]; p.idm.a_d = (double)a[3]; p.idm.rate_d = (double)cfg->rate; p.idm.delta_d = (double)a[4];
-  p.idm.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
-  p.idm.half_rate_d = 0.5 * (double)cfg->rate; p.idm.s0_z = (float)(0.0 + (double)a[8]);
+  fill_idm(p.idm, cfg->archetype, cfg->rate);
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
@@ -697,13 +706,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   CU(cudaSetDevice(device));
   CU(upload_math_consts());
   IdmConst c;
-  c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
-  { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
-  c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
-  c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
-  c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
-  c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
-  c.half_rate_d = 0.5 * (double)rate; c.s0_z = (float)(0.0 + (double)a[8]);
+  fill_idm(c, a, rate);
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
@@ -721,13 +724,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaSetDevice(device));
   CU(upload_math_consts());
   IdmConst c;
-  c.rate = rate; c.x_new = a[0]; c.v_new = a[1]; c.len = a[2]; c.a = a[3]; c.delta = a[4]; c.v0 = a[5]; c.T = a[7]; c.s0 = a[8];
-  { volatile float ab = a[3] * a[6]; c.two_sqrt_ab = (double)sqrtf(ab) * 2.0; }
-  c.rcp_two_sqrt_ab = 1.0 / c.two_sqrt_ab;
-  c.v0_d = (double)a[5]; c.rcp_v0 = 1.0 / (double)a[5];
-  c.s0_d = (double)a[8]; c.a_d = (double)a[3]; c.rate_d = (double)rate; c.delta_d = (double)a[4];
-  c.delta_is_four = (a[4] == 4.0f) && !getenv("TE_NO_POWF4_SHORTCUT");
-  c.half_rate_d = 0.5 * (double)rate; c.s0_z = (float)(0.0 + (double)a[8]);
+  fill_idm(c, a, rate);
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM

@@ -843,8 +843,8 @@ __global__ void te_powf4_exhaustive_kernel(unsigned long long tau, unsigned long
     if (!same) { diff++; if (acc) bad++; if (dist > maxd && dist != 0xffffffffu) maxd = dist; }
     if (!acc) slow++;
     // the step kernel's form of the filter (powf4_fast) must never accept an input whose shortcut differs
-    float fast2;
-    if (powf4_fast(r, fast2) && __float_as_uint(fast2) != __float_as_uint(ref)) bad++;
+    double pd2;
+    if (powf4_fast_d((double)r, pd2) && !(pd2 == (double)ref && __float_as_uint(__double2float_rn(pd2)) == __float_as_uint(ref))) bad++;
   }
   atomicAdd(&out[0], diff); atomicMax(&out[1], maxd); atomicAdd(&out[2], slow); atomicAdd(&out[3], bad);
 }
