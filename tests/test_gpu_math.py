@@ -181,3 +181,30 @@ def test_idm_with_and_without_powf4_shortcut_agree():
     finally:
         del os.environ["TE_NO_POWF4_SHORTCUT"]
     assert same_bits(a[0], b[0]).all() and same_bits(a[1], b[1]).all()
+
+
+def test_idm_pow2_forms_agree_with_conversions_and_oracle():
+    """T and rate powers of two: v * T and rate * v are taken as double products of the widened v (no conversion).
+    Same operands with the shortcut disabled (environment switch) and against the oracle, for the reference's
+    archetype and for another power-of-two pair, over speeds from subnormal to overflowing."""
+    import os
+    rng = np.random.RandomState(44)
+    n = 1_500_000
+    for rate, T in ((0.5, 2.0), (0.25, 4.0), (1.0, 0.5)):
+        arch = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, T, 1.0, 0.0], np.float32)
+        x = rng.uniform(-100, 400, n).astype(np.float32)
+        xl = (x + np.exp(rng.uniform(np.log(1e-6), np.log(1e4), n))).astype(np.float32)
+        v = np.exp(rng.uniform(np.log(1e-45), np.log(3e38), n)).astype(np.float32)
+        v[: n // 2] = rng.uniform(0, 20, n // 2).astype(np.float32)
+        v[n // 2: n // 2 + 5000] = 0.0
+        vl = rng.uniform(0, 20, n).astype(np.float32)
+        ll = np.full(n, 4, np.float32)
+        a = gpu_idm(rate, arch, xl, vl, ll, x, v)
+        os.environ["TE_NO_POW2_SHORTCUT"] = "1"
+        try:
+            b = gpu_idm(rate, arch, xl, vl, ll, x, v)
+        finally:
+            del os.environ["TE_NO_POW2_SHORTCUT"]
+        ox, ov = orc.sim_bulk(rate, xl, vl, ll, x, v, arch)
+        assert same_bits(a[0], b[0]).all() and same_bits(a[1], b[1]).all()
+        assert same_bits(a[0], ox).all() and same_bits(a[1], ov).all()
