@@ -266,6 +266,7 @@ def b200_arm(a):
     ticks = st1["ticks"] - st0["ticks"]
     asteps = st1["actor_steps"] - st0["actor_steps"]
     gen = st1["cars_generated"] - st0["cars_generated"]
+    seqfb = st1["seq_fallback_ticks"] - st0["seq_fallback_ticks"]
     # episode-return style reduction over NCCL/NVLink: a handful of scalars, the only collective of the path
     red = torch.tensor([float(vu), float(ticks), float(asteps), float(gen), float(st1["overflows"] - st0["overflows"])],
                        dtype=torch.float64, device=dev)
@@ -363,6 +364,7 @@ def b200_arm(a):
             "config": bench_config(a, w, E, occ),
             "env_steps_per_sec": {"ticks": ticks_all / sec, "actor_steps": asteps_all / sec},
             "ticks_per_actor_step": ticks_all / max(asteps_all, 1.0), "overflows_per_actor_step": ovf_all / max(asteps_all, 1.0),
+            "ordered_transfer_ticks_frac_rank0": seqfb / max(ticks, 1),
             "target_8gpu": 1e11, "frac_of_per_gpu_target": value / world / 1.25e10,
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

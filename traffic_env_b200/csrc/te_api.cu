@@ -41,8 +41,8 @@ struct te_handle {
   te_config cfg;
   int V, r, R, Rp, I, n_entry, G;
   int device;
-  cudaStream_t stream, stream2;
-  cudaEvent_t ev0, ev1, ev_fork, ev_join;
+  cudaStream_t stream, stream2, stream_copy;
+  cudaEvent_t ev0, ev1, ev_fork, ev_join, ev_copied, ev_slice[8];
   bool timed;
   StepParams base;  // everything except per-call pointers
   std::vector<int> dest, nexts, phases, entry;
@@ -164,8 +164,11 @@ static void free_handle(te_handle *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  for (cudaEvent_t e : h->ev_slice) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
   delete h;
 }
 
@@ -190,7 +193,9 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->d_nexts = h->d_up = h->d_entry_roads = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
   h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
   h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
-  h->stream = h->stream2 = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = nullptr; h->timed = false; h->trip_cap = 0;
+  h->stream = h->stream2 = h->stream_copy = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = h->ev_copied = nullptr;
+  for (cudaEvent_t &e : h->ev_slice) e = nullptr;
+  h->timed = false; h->trip_cap = 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUH(cudaSetDevice(h->device));
   CUH(upload_math_consts());
@@ -226,6 +231,9 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   const size_t E = (size_t)cfg->num_envs;
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+  CUH(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  for (cudaEvent_t &e : h->ev_slice) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
   CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -430,9 +438,9 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     h->timed = true;
     return 0;
   }
-  // Host buffers: the batch is launched in slices on two alternating streams, each slice followed by the
-  // device -> host copies of its observations / rewards / done flags, so the copies of one slice travel over
-  // PCIe while the next slices are simulated (envs are independent: any slicing gives the same results).
+  // Host buffers: the batch is launched in slices on two alternating streams (the tail of one slice overlaps the
+  // head of the next), and a third stream copies each finished slice's observations / rewards / done flags to the
+  // host while the following slices are simulated (envs are independent: any slicing gives the same results).
   const int E_i = h->cfg.num_envs;
   int nslice = E_i / 2048;
   nslice = nslice < 1 ? 1 : (nslice > 8 ? 8 : nslice);
@@ -440,21 +448,25 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
   CU(cudaEventRecord(h->ev_fork, st));               // actions (and the auto-reset) are complete on `st`
   CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   cudaStream_t lanes[2] = {st, h->stream2};
+  const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;
   for (int k = 0, e0 = 0; e0 < E_i; k++, e0 += per) {
     const int ne = (E_i - e0) < per ? (E_i - e0) : per;
     cudaStream_t cs = lanes[k & 1];
     p.env0 = e0;
     sv.fn<<<ne, h->Rp, smem, cs>>>(p);
     CU(cudaGetLastError());
-    const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;
+    CU(cudaEventRecord(h->ev_slice[k], cs));
+    CU(cudaStreamWaitEvent(h->stream_copy, h->ev_slice[k], 0));
     CU(cudaMemcpyAsync((char *)obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
-                       cudaMemcpyDeviceToHost, cs));
+                       cudaMemcpyDeviceToHost, h->stream_copy));
     CU(cudaMemcpyAsync(reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
-                       cudaMemcpyDeviceToHost, cs));
-    CU(cudaMemcpyAsync(done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, cs));
+                       cudaMemcpyDeviceToHost, h->stream_copy));
+    CU(cudaMemcpyAsync(done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
   }
   CU(cudaEventRecord(h->ev_join, h->stream2));
+  CU(cudaEventRecord(h->ev_copied, h->stream_copy));
   CU(cudaStreamWaitEvent(st, h->ev_join, 0));
+  CU(cudaStreamWaitEvent(st, h->ev_copied, 0));
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
   CU(cudaStreamSynchronize(st));
