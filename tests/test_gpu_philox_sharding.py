@@ -183,3 +183,33 @@ def test_device_buffers_and_host_buffers_agree():
         assert d_obs.cpu().numpy().tobytes() == obs.tobytes()
         assert d_rew.cpu().numpy().tobytes() == rew.tobytes()
         assert (d_done.cpu().numpy() == done).all()
+
+
+def test_host_path_slices_equal_single_launch():
+    """te_step with host buffers launches the batch in slices on two streams and copies each slice back while the
+    next ones run; te_step with device buffers is one launch.  Same seed -> identical obs / reward / done for
+    every env, including a batch size that does not divide into equal slices."""
+    import torch
+    from traffic_env_b200 import VecTrafficEnv
+    E = 8192 + 37
+    kw = dict(m=3, n=3, length=250.0, num_envs=E, arrivals="philox", seed=99, local_cars_per_sec=0.5,
+              ticks_per_step=10, remi=True)
+    a, b = VecTrafficEnv(**kw), VecTrafficEnv(**kw)
+    rng = np.random.RandomState(5)
+    init = rng.randint(2, size=(E, 9))
+    a.reset(init_phase=init)
+    b.reset(init_phase=init)
+    dev = torch.device("cuda", 0)
+    d_obs = torch.empty((E, a.obs_len), dtype=torch.float32, device=dev)
+    d_rew = torch.empty((E, 9), dtype=torch.float32, device=dev)
+    d_done = torch.empty((E,), dtype=torch.uint8, device=dev)
+    for s in range(12):
+        act = rng.randint(2, size=(E, 9)).astype(np.uint8)
+        obs, rew, done = a.step(act)
+        b.step_device(torch.from_numpy(act).to(dev), d_obs, d_rew, d_done)
+        torch.cuda.synchronize()
+        b.synchronize()
+        assert obs.tobytes() == d_obs.cpu().numpy().tobytes(), s
+        assert rew.tobytes() == d_rew.cpu().numpy().tobytes(), s
+        assert done.tobytes() == d_done.cpu().numpy().tobytes(), s
+    assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] > 0
