@@ -205,6 +205,8 @@ def b200_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." at NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     w = WORKLOADS[a.workload]
     E = a.envs or w["envs"]

@@ -177,9 +177,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 __device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+// Commit the bulk stores and wait until the copy engine has READ their shared-memory source (the CTA may then retire
+// and free its shared memory; the writes themselves complete before the grid does).
 __device__ __forceinline__ void bulk_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // Explicit shared-window accesses for the car loop: 32-bit shared addresses kept in registers (no generic-pointer
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     atomicAdd(&p.stats->cars_generated, (unsigned long long)s.misc[4]);
     if (s.misc[5]) atomicAdd(&p.stats->seq_fallback_ticks, (unsigned long long)s.misc[5]);
     if (s.misc[6]) atomicAdd(&p.stats->cars_exited, (unsigned long long)s.misc[6]);
-    bulk_commit_wait();  // the flush has left shared memory and reached HBM before the CTA retires
+    bulk_commit_wait();  // the flush has left shared memory before the CTA retires
   }
 }
 
