@@ -740,7 +740,9 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   fill_idm(c, a, rate);
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
+  int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
+  // latency study: TE_PEAK_WARPS_PER_SM = w runs w warps per SM (one CTA of w warps per SM) instead
+  if (const char *ev = getenv("TE_PEAK_WARPS_PER_SM")) { const int w = atoi(ev); if (w >= 1 && w <= 32) { threads = 32 * w; blocks = sms; } }
   float *sink = nullptr;
   CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
   cudaEvent_t e0, e1;
