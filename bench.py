@@ -205,9 +205,19 @@ def b200_arm(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." at NCCL_DEBUG=VERSION) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: whatever NCCL prints while the communicator comes up (its
+        # "NCCL version ..." banner at NCCL_DEBUG=VERSION/WARN) is sent to stderr by pointing fd 1 at fd 2 meanwhile
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     w = WORKLOADS[a.workload]
     E = a.envs or w["envs"]
     preroll = w["preroll"] if a.preroll < 0 else a.preroll
