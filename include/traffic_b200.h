@@ -119,9 +119,11 @@ int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *init_phase, i
    Buffers are copied; always host pointers. */
 int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t first_tick, int32_t horizon);
 
-/* One actor step = Repeater(k_ticks)._step (+ Remi when TE_REMI) for every env, one kernel launch
-   (traffic_test.py:37-64).  actions uint8[E, I] (non-zero = 1); obs float[E, 2r+I];
-   reward float[E, I]; done uint8[E].  The tick loop of an env stops after the tick that overflowed. */
+/* One actor step = Repeater(k_ticks)._step (+ Remi when TE_REMI) for every env (traffic_test.py:37-64).
+   actions uint8[E, I] (non-zero = 1); obs float[E, 2r+I]; reward float[E, I]; done uint8[E].  The tick loop
+   of an env stops after the tick that overflowed.  TE_DEVICE: one kernel launch on `stream`, asynchronous.
+   TE_HOST: synchronous; the batch is launched in slices and each finished slice's results are copied to the
+   host buffers while the next slices run (page-locked buffers, te_host_alloc, make those copies asynchronous). */
 int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
             int memspace, void *stream);
 
