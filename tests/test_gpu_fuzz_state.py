@@ -63,7 +63,10 @@ def load_oracle(o, st):
 @pytest.mark.parametrize("m,n,L,E,dense,ordered", [
     (3, 3, 250.0, 96, True, False), (3, 3, 250.0, 96, False, False), (3, 3, 250.0, 64, True, True),
     (2, 3, 100.0, 64, True, False), (1, 1, 60.0, 32, True, False), (10, 10, 500.0, 6, True, False),
-    (4, 2, 80.0, 48, False, True), (3, 2, 123.456, 64, True, False), (2, 2, 77.7, 48, True, False)])
+    (4, 2, 80.0, 48, False, True), (3, 2, 123.456, 64, True, False), (2, 2, 77.7, 48, True, False),
+    # one grid per kernel variant (row capacity 128 / 128 with Rp = 96 / 256 / 512 / 768 / 1024)
+    (5, 5, 150.0, 8, True, False), (4, 4, 90.0, 8, True, False), (7, 7, 120.0, 4, True, False),
+    (10, 11, 100.0, 3, True, False), (13, 13, 100.0, 2, True, False), (15, 15, 100.0, 2, False, False)])
 def test_random_states_tick_by_tick(m, n, L, E, dense, ordered):
     from traffic_env_b200 import VecTrafficEnv
     rng = np.random.RandomState(1000 * m + 10 * n + int(dense) + 2 * int(ordered))
