@@ -183,3 +183,45 @@ def test_fused_learn_switch_matches_raw_ticks():
         assert (sa["obs"][0][24:] == sb["obs"][0][24:]).all(), s   # detected | phase | elapsed
         checked += 1
     assert checked == 60
+
+
+@pytest.mark.parametrize("m,n,L,E", [(10, 10, 50.0, 3), (6, 5, 90.0, 4)])
+def test_validate_mode_larger_grids_vs_oracle(m, n, L, E):
+    """TE_VALIDATE on the larger kernel variants (third shared-memory plane): trip times of cars leaving the map
+    and the ring state against the oracle in validate mode, injected arrivals, 320 raw ticks."""
+    from oracle.oracle import OracleEnv
+    from traffic_env_b200 import VecTrafficEnv
+    from tests.golden_util import live_walk
+    rng = np.random.RandomState(100 * m + n)
+    T = 320
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, arrivals="injected", remi=False, validate=True)
+    I = env.intersections
+    scheds = [[list(rng.choice(env.entrypoints, size=rng.poisson(1.5))) for _ in range(T)] for _ in range(E)]
+    init = rng.randint(2, size=(E, I))
+    env.set_arrivals(scheds)
+    env.reset(init_phase=init)
+    oracles = []
+    for e in range(E):
+        o = OracleEnv(m, n, L, 0.5, validate=True)
+        o.reset(init[e])
+        oracles.append(o)
+    act = rng.randint(2, size=(E, I))
+    for t in range(T):
+        if t % 10 == 0:
+            act = rng.randint(2, size=(E, I))
+        obs, rew, done = env.step_raw(act)
+        for e, o in enumerate(oracles):
+            o.step(act[e], scheds[e][t])
+            assert (obs[e] == o.obs).all(), (e, t)
+    envs, trips = env.trip_times()
+    st = env.get_state()
+    total = 0
+    for e, o in enumerate(oracles):
+        want = np.asarray(o.trip_times(), np.float64)
+        got = np.asarray(trips[np.asarray(envs) == e], np.float64)
+        assert got.tobytes() == want.tobytes(), e
+        total += len(want)
+        gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+        ox, ov = o.live_state()
+        assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes()
+    assert total > 20
