@@ -14,11 +14,11 @@
 //   phase A  (warp-local, no CTA barrier inside)
 //     - lane = road: entry arrivals -> add_car                 (traffic_env.py:274-283, 97-114)
 //     - lane = road: virtual leader x from the light state     (update_lights, :81-94)
-//     - the warp's live cars are compacted into lanes in ring order (warp prefix sum over the
-//       per-road counts + a per-warp item list), 32 cars per chunk, every lane busy; each car
-//       reads its predecessor's pre-update (x, v) - chunks run back to front so the in-place
-//       update is the Jacobi update of sim (:50-62) / move_cars (:187-212); waiting/detected
-//       counts come back to the road lanes through ballots
+//     - car loop: the warp's live cars, road after road in ring order, form one list (warp prefix sum over
+//       the per-road counts); every lane simulates a contiguous run of it, keeping the pre-update (x, v, l)
+//       of the car ahead in registers from its previous iteration, so the in-place update is the Jacobi
+//       update of sim (:50-62) / move_cars (:187-212); a per-warp road table holds the shared-memory
+//       addresses a run walks; waiting/detected counts go back to the road lanes with shared-memory adds
 //     - lane = road: pops - leading advances past cars with x > length (advance_finished_cars, :117-135)
 //   barrier
 //   phase C  (lane = destination road)
