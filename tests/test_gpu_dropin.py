@@ -218,3 +218,41 @@ def test_random_entry_matches_reference_recording(dropin):
                 i += 1
     finally:
         FLAGS.entry, FLAGS.local_cars_per_sec = "all", 0.12
+
+
+@pytest.mark.parametrize("learn_switch", [False, True])
+def test_fused_step_host_mirror_equals_device_state(dropin, learn_switch):
+    """The fused Repeater step refreshes the caller-visible int32 obs (detected | phase | elapsed) from closed
+    forms on the host when no ring overflowed; with TRAFFIC_B200_NO_HOST_MIRROR it reads the device state back
+    instead.  Both must agree at every step, including steps that overflow and resets in between."""
+    gym, GridRoad, FLAGS = dropin
+    from traffic_env_b200.wrappers import Remi, Repeater
+    old_ls, old_rate = FLAGS.learn_switch, FLAGS.local_cars_per_sec
+    FLAGS.learn_switch, FLAGS.local_cars_per_sec = learn_switch, 0.35   # heavy arrivals: some steps overflow
+    try:
+        def run(mirror_off):
+            if mirror_off:
+                os.environ["TRAFFIC_B200_NO_HOST_MIRROR"] = "1"
+            try:
+                np.random.seed(4)
+                base = new_env(gym, GridRoad, seed=21)
+                env = Remi(Repeater(10)(base))
+                rng = np.random.RandomState(8)
+                out = []
+                env.reset()
+                for s in range(150):
+                    a = rng.randint(2, size=9) if s % 4 else rng.rand(9) < 0.5
+                    obs, rew, done, _ = env.step(a)
+                    out.append((obs.copy(), rew.copy(), done, base.obs.copy(), float(base.steps)))
+                    if done:
+                        env.reset()
+                return out
+            finally:
+                os.environ.pop("TRAFFIC_B200_NO_HOST_MIRROR", None)
+        fast, slow = run(False), run(True)
+        assert any(d for _, _, d, _, _ in fast) and not all(d for _, _, d, _, _ in fast)
+        for s, (f, g) in enumerate(zip(fast, slow)):
+            assert f[0].tobytes() == g[0].tobytes() and f[1].tobytes() == g[1].tobytes() and f[2] == g[2], s
+            assert (f[3] == g[3]).all() and f[4] == g[4], s
+    finally:
+        FLAGS.learn_switch, FLAGS.local_cars_per_sec = old_ls, old_rate

@@ -68,12 +68,23 @@ def main(argv=None):
     policy = controllers(env, a.spacing)[a.trainer]
     episode_len = int(a.episode_secs / a.light_secs)
     mean = var = 0.0
+    import time
+    t0, total_steps = time.perf_counter(), 0
     for it in range(1, a.episodes + 1):
         reward, steps = run_episode(env, policy, episode_len, a.gamma, bool(a.print_discounted))
+        if it == 1:   # the first episode creates the CUDA context and the device handle: keep it out of the rate
+            t0, total_steps = time.perf_counter(), 0
+        else:
+            total_steps += steps
         mean = (reward + (it - 1) * mean) / it
         if it >= 2:
             var = (it - 2) / (it - 1) * var + (reward - mean) ** 2 / it
         print("Reward %2f\t Mean %2f\t Std %2f\t (%d actor steps)" % (reward, mean, math.sqrt(var), steps))
+    dt = time.perf_counter() - t0
+    k = int(a.light_secs / a.rate)
+    if total_steps:
+        print("%d actor steps in %.2f s after the first episode: %.0f actor steps/s, up to %.0f physics ticks/s "
+              "(single env, one launch per actor step)" % (total_steps, dt, total_steps / dt, total_steps * k / dt))
     return mean
 
 

@@ -219,16 +219,36 @@ class TrafficEnv(gym.Env):
 
     def step_repeated(self, action, repeat_count):
         """Repeater(repeat_count)._step fused into one launch (traffic_test.py:37-56): returns the float
-        observation [passed summed | detected | elapsed/100 * (2*phase-1)], the summed env reward and done."""
+        observation [passed summed | detected | elapsed/100 * (2*phase-1)], the summed env reward and done.
+
+        The int32 `obs` views the callers hold (current_phase, elapsed, detected) are refreshed WITHOUT reading
+        the device state back when all `repeat_count` ticks ran (no ring overflow): the light state of a constant
+        action is a closed form of the tick count (traffic_env.py:225-232) and `detected` comes back in the float
+        observation.  A step that overflowed (the tick loop stopped early) reads the state from the device."""
         sim = self._device()
         self._ensure_schedule(repeat_count)
         self._push_if_dirty()
-        t0 = sim.stats()["ticks"]
-        obs, rew, done = sim.step(self._as_action(action), k=repeat_count)
-        ticks = sim.stats()["ticks"] - t0
-        st = sim.get_state(0, 1)
-        raw = st["obs"][0]
-        raw[:self.graph.train_roads] = 0  # per-tick `passed` of the last tick is not kept by the fused path
+        act = self._as_action(action)
+        obs, rew, done = sim.step(act, k=repeat_count)
+        r, i = self.graph.train_roads, self.graph.intersections
+        if not done[0] and not self._key[-1] and not os.environ.get("TRAFFIC_B200_NO_HOST_MIRROR"):
+            a = act[0].astype(np.int32)
+            raw = self._mirror.copy()
+            ph, el = raw[2 * r:2 * r + i], raw[2 * r + i:]
+            if FLAGS.learn_switch:                       # the action toggles: elapsed restarts at every tick it is set
+                el[:] = np.where(a != 0, 0, el + repeat_count)
+                ph[:] = ph ^ (a * (repeat_count & 1))
+            else:                                        # first tick: change = phase xor action, then `action` holds
+                el[:] = (el + 1) * (ph == a) + (repeat_count - 1)
+                ph[:] = a
+            raw[:r] = 0      # per-tick `passed` of the last tick is not kept by the fused path
+            raw[r:2 * r] = obs[0, r:2 * r].astype(np.int32)
+            ticks = repeat_count
+        else:
+            st = sim.get_state(0, 1)
+            raw = st["obs"][0]
+            raw[:r] = 0
+            ticks = int(round(float(st["steps"][0]) - float(self.steps)))
         self._pull(raw, rew[0], ticks)
         return obs[0].copy(), self.rewards, bool(done[0])
 
