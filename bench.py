@@ -183,13 +183,13 @@ def reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
-def bench_config(a, w, envs, occ):
+def bench_config(a, w, envs, occ, rows_padded=None):
     return {"workload": a.workload, "grid": "%dx%d" % (w["m"], w["n"]), "road_length_m": w["length"],
             "envs_per_gpu": envs, "policy": "greedy(spacing=%d)" % SPACING, "ticks_per_actor_step": K_TICKS,
             "arrivals": "philox, local_cars_per_sec=%.2f (reference default)" % w["lcps"],
             "wrappers": "Remi(Repeater(10))", "reset": "none (env keeps stepping after overflow, as the reference env does)",
             "steady_state_cars_per_env": occ, "l2": "state is %.2f GB per GPU, far larger than the 126 MB L2"
-            % (envs * ((w["m"] * w["n"] * 4 + 2 * w["m"] + 2 * w["n"] + 7) // 8 * 8) * 160 / 1e9)}
+            % (envs * (rows_padded or (w["m"] * w["n"] * 4 + 2 * w["m"] + 2 * w["n"] + 31) // 32 * 32) * 160 / 1e9)}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -373,7 +373,7 @@ def b200_arm(a):
             "metric": "vehicle_updates_per_sec", "value": value, "unit": "vehicle-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": bench_config(a, w, E, occ),
+            "config": bench_config(a, w, E, occ, env.roads_padded),
             "env_steps_per_sec": {"ticks": ticks_all / sec, "actor_steps": asteps_all / sec},
             "ticks_per_actor_step": ticks_all / max(asteps_all, 1.0), "overflows_per_actor_step": ovf_all / max(asteps_all, 1.0),
             "ordered_transfer_ticks_frac_rank0": seqfb / max(ticks, 1),

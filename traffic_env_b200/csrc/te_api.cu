@@ -202,6 +202,17 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   const int m = cfg->m, n = cfg->n;
   h->V = m * n; h->I = h->V; h->r = 4 * h->V; h->R = h->r + 2 * n + 2 * m;
   h->Rp = (h->R + GROUP_ROADS - 1) / GROUP_ROADS * GROUP_ROADS;
+  {
+    // Whole groups of four warps keep the SM's four schedulers evenly loaded (a 14-warp CTA puts 4, 4, 3, 3 warps on
+    // them; two such CTAs 8, 8, 6, 6): pad to a multiple of 128 threads when that costs at most 20 % more rows.
+    // 10x10 grid: 440 roads -> 512 threads, 16 warps, 64 registers: +1.7 % (measured A/B, 3 runs each).
+    const int rp128 = (h->R + 127) / 128 * 128;
+    if (rp128 * 5 <= h->R * 6) h->Rp = rp128;
+  }
+  if (const char *ev = getenv("TE_RP_ALIGN")) {   // study knob: pad the CTA to a multiple of this many threads
+    const int al = atoi(ev);
+    if (al >= 32 && al % 32 == 0 && al <= 1024) h->Rp = (h->R + al - 1) / al * al;
+  }
   h->G = h->Rp / GROUP_ROADS;
   // topology (roadgraph.py:35-39, 42-51)
   h->dest.resize(h->R); h->nexts.resize(h->R); h->phases.resize(h->R);

@@ -68,6 +68,7 @@ class VecTrafficEnv(object):
         check(L.te_get_dims(self._h, C.byref(d)))
         self.m, self.n = d.m, d.n
         self.intersections, self.train_roads, self.roads = d.intersections, d.train_roads, d.roads
+        self.roads_padded = d.roads_padded
         self.num_envs, self.num_entry = d.num_envs, d.num_entry
         self.obs_raw_len, self.obs_len = d.obs_raw, d.obs_actor
         self.ticks_per_step = int(ticks_per_step)
