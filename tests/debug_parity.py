@@ -1,5 +1,5 @@
 """Developer tool: run a raw golden fixture on the GPU and on the oracle side by side and print
-the first field that differs.  Usage: python tools/debug_parity.py tests/golden/NAME.npz [max_ticks]"""
+the first field that differs.  Usage: python tests/debug_parity.py tests/golden/NAME.npz [max_ticks]"""
 import os
 import sys
 
