@@ -39,7 +39,7 @@ static int fail(const char *fmt, ...) {
 
 struct te_handle {
   te_config cfg;
-  int V, r, R, Rp, I, n_entry, G;
+  int V, r, R, Rp, I, n_entry;
   int device;
   cudaStream_t stream, stream2, stream_copy;
   cudaEvent_t ev0, ev1, ev_fork, ev_join, ev_copied, ev_slice[64];
@@ -52,7 +52,7 @@ struct te_handle {
   uint8_t *phase, *passed_dst;
   EnvScalars *env;
   DeviceStats *stats;
-  short *d_nexts, *d_up, *d_entry_roads;
+  short *d_nexts, *d_up;
   signed char *d_entry_idx;
   long long *d_sched_off;
   short *d_sched_roads;
@@ -156,7 +156,7 @@ static void free_handle(te_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   void *ptrs[] = {h->w, h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
-                  h->d_entry_roads, h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
+                  h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
                   h->d_done, h->d_mask, h->d_init_phase, h->d_reward, h->d_obs_i /* d_obs_f aliases it */, h->d_cars,
                   h->d_trips, h->d_trip_count};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -190,7 +190,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   memset((void *)&h->base, 0, sizeof(h->base));
   h->cfg = *cfg; h->device = cfg->device;
   h->x = h->v = h->w = nullptr; h->elapsed = nullptr; h->phase = h->passed_dst = nullptr; h->env = nullptr; h->stats = nullptr;
-  h->d_nexts = h->d_up = h->d_entry_roads = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
+  h->d_nexts = h->d_up = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
   h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
   h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
   h->stream = h->stream2 = h->stream_copy = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = h->ev_copied = nullptr;
@@ -213,7 +213,6 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
     const int al = atoi(ev);
     if (al >= 32 && al % 32 == 0 && al <= 1024) h->Rp = (h->R + al - 1) / al * al;
   }
-  h->G = h->Rp / GROUP_ROADS;
   // topology (roadgraph.py:35-39, 42-51)
   h->dest.resize(h->R); h->nexts.resize(h->R); h->phases.resize(h->R);
   std::vector<short> nx(h->Rp, -1), up(h->Rp, -1);
@@ -236,8 +235,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (((spec >> 3) & 1) == 0) for (int i = 0; i < n; i++) h->entry.push_back(3 * v + n * (m - 1) + i);
   h->n_entry = (int)h->entry.size();
   if (h->n_entry > 127) { free_handle(h); return fail("te_create: more than 127 entry roads"); }
-  std::vector<short> eroads(h->n_entry > 0 ? h->n_entry : 1, 0);
-  for (int k = 0; k < h->n_entry; k++) { eroads[k] = (short)h->entry[k]; eidx[h->entry[k]] = (signed char)k; }
+  for (int k = 0; k < h->n_entry; k++) eidx[h->entry[k]] = (signed char)k;
 
   const size_t E = (size_t)cfg->num_envs;
   CUH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -259,7 +257,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(dalloc(&h->elapsed, E * h->I)); CUH(dalloc(&h->phase, E * h->I)); CUH(dalloc(&h->passed_dst, E * h->I));
   CUH(dalloc(&h->env, E)); CUH(dalloc(&h->stats, 1));
   CUH(dalloc(&h->d_nexts, (size_t)h->Rp)); CUH(dalloc(&h->d_up, (size_t)h->Rp));
-  CUH(dalloc(&h->d_entry_idx, (size_t)h->Rp)); CUH(dalloc(&h->d_entry_roads, eroads.size()));
+  CUH(dalloc(&h->d_entry_idx, (size_t)h->Rp));
   CUH(dalloc(&h->d_actions, E * h->I)); CUH(dalloc(&h->d_done, E)); CUH(dalloc(&h->d_mask, E));
   CUH(dalloc(&h->d_init_phase, E * h->I));
   CUH(dalloc(&h->d_obs_i, E * (2 * h->r + 2 * h->I)));
@@ -268,7 +266,6 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaMemcpy(h->d_nexts, nx.data(), nx.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_up, up.data(), up.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_entry_idx, eidx.data(), eidx.size(), cudaMemcpyHostToDevice));
-  CUH(cudaMemcpy(h->d_entry_roads, eroads.data(), eroads.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemset(h->stats, 0, sizeof(DeviceStats)));
   CUH(cudaMemset(h->x, 0, E * h->Rp * CAP * sizeof(float)));
   CUH(cudaMemset(h->v, 0, E * h->Rp * CAP * sizeof(float)));
@@ -296,11 +293,12 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaMemcpy(h->env, es.data(), E * sizeof(EnvScalars), cudaMemcpyHostToDevice));
 
   StepParams &p = h->base;
-  p.V = h->V; p.r = h->r; p.R = h->R; p.Rp = h->Rp; p.I = h->I; p.n_entry = h->n_entry; p.G = h->G;
-  p.num_envs = cfg->num_envs; p.length = cfg->length; p.det_thr = (double)cfg->length - 10.0;
+  p.V = h->V; p.r = h->r; p.R = h->R; p.Rp = h->Rp; p.I = h->I; p.n_entry = h->n_entry;
+  p.num_envs = cfg->num_envs; p.length = cfg->length;
   {
-    float f = (float)p.det_thr;                       // round to nearest, then step down if that went above
-    if ((double)f > p.det_thr) f = nextafterf(f, -INFINITY);
+    const double det_thr = (double)cfg->length - 10.0;
+    float f = (float)det_thr;                         // round to nearest, then step down if that went above
+    if ((double)f > det_thr) f = nextafterf(f, -INFINITY);
     p.det_thr_f = f;
   }
   p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
@@ -309,7 +307,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
-  p.entry_roads = h->d_entry_roads; p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
+  p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
   p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0; p.sched_first = 0;
 

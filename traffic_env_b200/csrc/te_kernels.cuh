@@ -70,12 +70,12 @@ struct TripRecord {
 };
 
 struct StepParams {
-  int V, r, R, Rp, I, n_entry, G;
+  int V, r, R, Rp, I, n_entry;
   int num_envs;
   int env0;               // first env of this launch (te_step with host buffers launches the batch in slices)
   float length;
-  double det_thr;         // (double)length - 10.0  (traffic_env.py:201: float32 - int64 types as float64)
-  float det_thr_f;        // largest float <= det_thr: for every float x, (double)x > det_thr  <=>  x > det_thr_f
+  float det_thr_f;        // largest float <= (double)length - 10.0 (traffic_env.py:201: float32 - int64 types as float64):
+                          // for every float x, (double)x > (double)length - 10.0  <=>  x > det_thr_f
   int flags, arrival_mode, K, raw, episode_len;
   float gamma;
   IdmConst idm;
@@ -92,7 +92,6 @@ struct StepParams {
   // topology (HBM, read-only)
   const short *nexts, *up;      // [Rp], -1 = none
   const signed char *entry_idx; // [Rp], index into the entry list or -1
-  const short *entry_roads;     // [n_entry]
   // per-call I/O (device pointers)
   const uint8_t *actions;       // [E][I]
   float *obs_f;                 // [E][2r+I]   (fused actor step)
