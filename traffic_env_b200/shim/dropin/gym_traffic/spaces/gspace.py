@@ -1,30 +1,36 @@
 """GSpace: the multi-agent "generic space" every agent of the reference talks to
-(reference gym_traffic/spaces/gspace.py:4-22).  Semantics preserved exactly, including that
-sample() draws from the GLOBAL numpy RNG with the dtype of `limit`."""
+(reference gym_traffic/spaces/gspace.py:4-22): a box of `shape` whose elements are integers (or floats) below
+`limit`, typed by `limit`'s dtype.  Semantics preserved exactly - including that sample() draws from the GLOBAL
+numpy RNG with that dtype (action sequences of seeded runs depend on it) and that `contains` compares the array
+shape with the (list) shape as given."""
 import gym
 import numpy as np
 
 
 class GSpace(gym.Space):
     def __init__(self, shape, limit):
-        self.shape = shape
-        self.limit = limit
+        self.shape, self.limit = shape, limit
         self.size = int(np.prod(shape))
 
+    @property
+    def dtype(self):
+        return self.limit.dtype
+
     def sample(self):
-        return np.random.randint(self.limit, size=self.shape, dtype=self.limit.dtype)
+        draw = np.random.randint                       # module-level RandomState, like the reference (:14)
+        return draw(self.limit, size=self.shape, dtype=self.dtype)
 
     def contains(self, x):
         return x.shape == self.shape
 
     def empty(self):
-        return np.empty(self.shape, dtype=self.limit.dtype)
+        return np.empty(self.shape, self.dtype)
 
     def to_action(self, a):
-        return np.reshape(a, self.shape).astype(self.limit.dtype)
+        return np.asarray(a).reshape(self.shape).astype(self.dtype)
 
     def replicated(self, n):
-        return GSpace([n] + self.shape, self.limit)
+        return GSpace([n, *self.shape], self.limit)
 
     def __repr__(self):
         return "GSpace(%r, %r)" % (self.shape, self.limit)
