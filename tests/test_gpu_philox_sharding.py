@@ -213,3 +213,43 @@ def test_host_path_slices_equal_single_launch():
         assert rew.tobytes() == d_rew.cpu().numpy().tobytes(), s
         assert done.tobytes() == d_done.cpu().numpy().tobytes(), s
     assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] > 0
+
+
+@pytest.mark.parametrize("m,n,L,E,S,lcps", [(3, 3, 250.0, 48, 1200, 0.12), (10, 10, 500.0, 4, 330, 0.12), (5, 4, 150.0, 16, 400, 0.2)])
+def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps):
+    """Long runs (up to 12000 ticks per env, no reset: the env keeps stepping after overflows, greedy lights every
+    third step as in the bench) against the oracle on the same Philox stream: every actor step's observation,
+    reward and done flag, and the final ring state, bit for bit.  Reaches the states a short run does not: dense
+    steady state, wrapped rings everywhere, the rare full-powf and generic-arithmetic lanes."""
+    from traffic_env_b200 import VecTrafficEnv
+    from traffic_env_b200.arrivals import gap_cdf
+    from tests.golden_util import live_walk
+    K, I = 10, m * n
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, arrivals="philox", seed=7, local_cars_per_sec=lcps,
+                        ticks_per_step=K, remi=True)
+    init = np.random.RandomState(2).randint(2, size=(E, I))
+    env.reset(init_phase=init)
+    cdf = gap_cdf(env.cars_per_sec * 0.5)
+    oracles = []
+    for e in range(E):
+        o = OracleEnv(m, n, L, 0.5)
+        o.reset(init[e])
+        o.philox_seed(7, e, cdf)
+        oracles.append(o)
+    act = np.zeros((E, I), np.uint8)
+    for s in range(S):
+        if s % 3 == 0:
+            act = env.greedy_actions().copy()
+            for e, o in enumerate(oracles):   # the device controller == greedy.py:14-16 on the oracle's counts
+                assert (act[e] == (o.cars_on_roads().reshape(-1, 4).dot([1, 1, -1, -1]) < 0)).all(), (e, s)
+        obs, rew, done = env.step(act)
+        for e, o in enumerate(oracles):
+            oo, orw, od = o.actor_step_philox(act[e].astype(np.int32), K, use_remi=True)
+            assert obs[e].tobytes() == oo.tobytes() and rew[e].tobytes() == orw.tobytes() and bool(done[e]) == od, (e, s)
+    st = env.get_state()
+    for e, o in enumerate(oracles):
+        assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all()
+        gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+        ox, ov = o.live_state()
+        assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes()
+    assert env.stats()["vehicle_updates"] == sum(o.vehicle_updates for o in oracles)
