@@ -686,7 +686,7 @@ extern "C" int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  const double bytes = 2.0 /* planes */ * 2.0 /* in + out */ * (double)h->cfg.num_envs * h->Rp * CAP * 4.0 * repeats;
+  const double bytes = 2.0 /* planes */ * 2.0 /* in + out */ * (double)h->cfg.num_envs * h->R * CAP * 4.0 * repeats;
   *gbytes_per_sec = bytes / (ms * 1e-3) / 1e9;
   return 0;
 }

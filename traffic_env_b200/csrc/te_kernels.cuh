@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   EnvScalars *es = p.env + env;
 
   // ------------------------------------------------------------ prologue: stage the env
-  const uint32_t plane_bytes = (uint32_t)p.Rp * CAP * 4;  // multiple of 16: Rp is a multiple of 32 roads of 80 B
+  // only the R real roads travel: the padding rows (threads R .. Rp-1) are set up in shared memory below
+  const uint32_t plane_bytes = (uint32_t)p.R * CAP * 4;   // multiple of 16: rows of 80 B
   if (tid == 0) {
     mbar_init(s.mbar, 1);
     fence_proxy_async();
@@ -364,6 +365,10 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   }
   __syncthreads();
   mbar_wait(s.mbar, 0);  // the ring planes have landed
+  if (tid >= p.R) {      // a padding row: an empty ring behind a free road, like te_reset leaves one
+    s.xs[tid * CAP] = __uint_as_float(pack_meta(1, 1, 0)); s.vs[tid * CAP] = __int_as_float(0);
+    s.xs[tid * CAP + 1] = INF; s.vs[tid * CAP + 1] = 0.f;
+  }
 
   // ---- road -> (warp, lane) assignment for this launch, balanced by car count: counting sort of the roads by
   // their current number of cars (0..18), then dealt to the warps in snake order, so every warp simulates
@@ -689,7 +694,7 @@ __global__ void te_stage_kernel(const StepParams p, int validate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   (void)validate;
   const int env = blockIdx.x;
-  const uint32_t plane_bytes = (uint32_t)p.Rp * CAP * 4;
+  const uint32_t plane_bytes = (uint32_t)p.R * CAP * 4;   // the real roads, like the step kernel
   float *xs = reinterpret_cast<float *>(smem_raw), *vs = reinterpret_cast<float *>(smem_raw + plane_bytes);
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw + 2 * plane_bytes);
   if (threadIdx.x == 0) {
