@@ -8,7 +8,7 @@ the ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports it either: the
 reference cannot travel to the GPU box.
 
 What is needed to import the reference unchanged:
-  * an old-API ``gym`` (traffic_env_b200/shim/gym),
+  * an old-API ``gym`` (tests/support/gym_compat),
   * ``np.bool8`` (removed in numpy 2; used at traffic_env.py:380),
   * ``alg_flags`` imported before stepping (registers FLAGS.mode, read at
     traffic_env.py:240),
@@ -24,7 +24,7 @@ import types
 
 REFERENCE_DIR = os.environ.get("TRAFFIC_ENV_REFERENCE", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SHIM = os.path.join(os.path.dirname(_HERE), "traffic_env_b200", "shim")
+_SUPPORT = os.path.join(os.path.dirname(_HERE), "tests", "support")
 
 
 def available():
@@ -46,7 +46,7 @@ def load():
     import numpy as np
     if not hasattr(np, "bool8"):
         np.bool8 = np.bool_
-    gym_dir = os.path.join(_SHIM, "gym_compat")
+    gym_dir = os.path.join(_SUPPORT, "gym_compat")
     for p in (REFERENCE_DIR, gym_dir):
         if p not in sys.path:
             sys.path.insert(0, p)

@@ -1,6 +1,6 @@
-"""Launcher for the reference's baseline controllers on the B200 env:
+"""TEST SUPPORT - launcher for the reference's baseline controllers on the B200 env:
 
-    python -m traffic_env_b200.run --trainer fixed|random|greedy|spacedgreedy|const0|const1 [--episodes N] [...]
+    python -m tests.support.run_baselines --trainer fixed|random|greedy|spacedgreedy|const0|const1 [--episodes N] [...]
 
 Mirrors `python traffic_test.py --trainer X` (traffic_test.py:93-95, alg_flags.py:46-49) for the TensorFlow-free
 controllers (algorithms/{fixed,random,greedy,spacedgreedy,const0,const1}.py): same env factory, same episode loop,
@@ -57,10 +57,10 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--remi", type=int, default=1)
     a = ap.parse_args(argv)
-    import traffic_env_b200.install as inst
-    inst.install()
+    from tests.support import install_dropin
+    install_dropin()
     from args import FLAGS
-    from traffic_env_b200.wrappers import make_env
+    from tests.support.wrappers_ref import make_env
     FLAGS.rate, FLAGS.local_cars_per_sec, FLAGS.poisson, FLAGS.entry, FLAGS.learn_switch = a.rate, a.local_cars_per_sec, True, "all", False
     m, n, length = (int(v) for v in a.grid.split("x"))
     np.random.seed(a.seed)

@@ -16,8 +16,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.fixture(scope="module")
 def dropin():
-    import traffic_env_b200.install as inst
-    inst.install()
+    from tests.support import install_dropin
+    install_dropin()
     import gym
     import gym_traffic  # noqa: F401
     from args import FLAGS
@@ -97,7 +97,7 @@ def test_fused_wrappers_match_tick_loop(dropin):
 
 def test_agent_loop_contracts(dropin):
     gym, GridRoad, FLAGS = dropin
-    from traffic_env_b200.wrappers import make_env
+    from tests.support.wrappers_ref import make_env
     FLAGS.light_iterations = 10
     env = make_env(seed=5)
     # fixed.py: float64 0./1. actions alternating every `spacing` steps
@@ -142,7 +142,7 @@ def test_full_wrapper_stack_and_launcher(dropin):
     """traffic_test.make_env's optional layers (Warmup, Localize, Squish, History, UnGSpace) on the B200 env, and
     the baseline-controller launcher."""
     gym, GridRoad, FLAGS = dropin
-    from traffic_env_b200.wrappers import make_env
+    from tests.support.wrappers_ref import make_env
     np.random.seed(4)
     env = make_env(seed=1, light_iterations=10, warmup_lights=2, local_weight=3, history=4)
     obs = env.reset()

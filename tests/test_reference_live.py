@@ -75,6 +75,7 @@ for stub in ("tensorflow", "matplotlib", "matplotlib.pyplot"):     # inert: the 
         importlib.import_module(stub)
     except Exception:
         sys.modules[stub] = types.ModuleType(stub)
+sys.path.insert(0, os.path.join(%(root)r, 'tests', 'support', 'gym_compat'))   # the only stand-in: an old-API gym
 import traffic_env_b200.install as inst
 dropin = inst.install(reference_dir=%(ref)r)
 sys.argv = ["traffic_test.py", "--trainer", "fixed"]

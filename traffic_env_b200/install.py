@@ -1,28 +1,19 @@
-"""Put the drop-in `gym_traffic` package (and, when missing, compat `gym` / `args`) on sys.path.
+"""Put the drop-in `gym_traffic` package on sys.path, ahead of any other `gym_traffic`.
 
-    import traffic_env_b200.install as inst; inst.install()
+    import traffic_env_b200.install as inst; inst.install(reference_dir="/path/to/traffic-env")
     import gym, gym_traffic            # gym_traffic.envs.TrafficEnv now steps on the B200
 
-With the reference checkout also on sys.path (after ours), its wrappers/ and algorithms/ stay
-importable as gym_traffic.wrappers / gym_traffic.algorithms: only the simulator modules
-(gym_traffic/__init__.py, envs/, spaces/) are replaced.
+Only the simulator modules are replaced (gym_traffic/__init__.py, envs/, spaces/).  With the reference
+checkout given (or already on sys.path) its args.py, wrappers/ and algorithms/ are reused unchanged:
+`gym_traffic.wrappers.*` / `gym_traffic.algorithms.*` resolve there.  `gym` (the old `_step/_reset` API the
+reference is written against) and the reference's `args` module must be importable; this package does not
+ship stand-ins for them (the test-suite has its own under tests/support/, because the GPU box has neither).
 """
 import importlib
 import os
 import sys
 
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
-DROPIN = os.path.join(_SHIM, "dropin")
-GYM_COMPAT = os.path.join(_SHIM, "gym_compat")
-ARGS_COMPAT = os.path.join(_SHIM, "args_compat")
-
-
-def _importable(name):
-    try:
-        importlib.import_module(name)
-        return True
-    except Exception:
-        return False
+DROPIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim", "dropin")
 
 
 def install(reference_dir=None):
@@ -31,12 +22,11 @@ def install(reference_dir=None):
         sys.path.append(reference_dir)
     if reference_dir:
         os.environ["TRAFFIC_ENV_REFERENCE"] = reference_dir
-    if not _importable("gym") or not hasattr(sys.modules["gym"], "Env") or not hasattr(sys.modules["gym"].Env, "_step"):
-        for k in [k for k in sys.modules if k == "gym" or k.startswith("gym.")]:
-            del sys.modules[k]
-        sys.path.insert(0, GYM_COMPAT)
-    if not _importable("args"):
-        sys.path.insert(0, ARGS_COMPAT)
+    for name, what in (("gym", "an old-API gym (gym.Env with _step/_reset)"), ("args", "the reference's args.py")):
+        try:
+            importlib.import_module(name)
+        except Exception as ex:
+            raise ImportError("traffic_env_b200.install: %s must be importable (%s: %s)" % (what, type(ex).__name__, ex))
     for k in [k for k in sys.modules if k == "gym_traffic" or k.startswith("gym_traffic.")]:
         del sys.modules[k]
     if DROPIN in sys.path:

@@ -18,6 +18,18 @@ import numpy as np
 from .vec_env import VecTrafficEnv
 
 
+def _gspace_class():
+    """The drop-in's GSpace (shim/dropin/gym_traffic/spaces/gspace.py), loaded by path so that the pool does not
+    need the `gym_traffic` package (whose __init__ imports gym) to be installed."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim", "dropin", "gym_traffic", "spaces", "gspace.py")
+    spec = importlib.util.spec_from_file_location("traffic_env_b200._gspace", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.GSpace
+
+
 class _Graph(object):
     def __init__(self, vec):
         self.m, self.n = vec.m, vec.n
@@ -29,7 +41,7 @@ class EnvSlot(object):
     """What one learner thread sees: the gym-style API of a single wrapped traffic env."""
 
     def __init__(self, pool, index):
-        from .spaces import GSpaceLike
+        GSpaceLike = _gspace_class()
         self.pool, self.index = pool, index
         v = pool.vec
         self.action_space = GSpaceLike([v.intersections], np.int32(2))

@@ -1,8 +1,8 @@
 """GridRoad: m x n grid of intersections joined by one-way roads without turns.
 
 Host-side table builder with the attribute names of reference gym_traffic/envs/roadgraph.py:25-64
-(`len, m, n, train_roads, roads, intersections, phases, dest, nexts, entrypoints, locs`,
-`generate_entrypoints`, `get_next`).  Road id = d * V + row * n + col with V = m * n and d in
+(`len, m, n, train_roads, roads, intersections, phases, dest, nexts, entrypoints`,
+`generate_entrypoints`, `get_next`; `locs` - the renderer's segment coordinates, roadgraph.py:5-22 - is out of scope).  Road id = d * V + row * n + col with V = m * n and d in
 {0: east-bound, 1: west-bound, 2: south-bound (row + 1), 3: north-bound (row - 1)}; ids >= 4V are
 the 2n + 2m exit roads.  The device builds the same tables in te_create (te_api.cu) - tests compare.
 """
@@ -21,7 +21,6 @@ class GridRoad(object):
         self.phases = (ids // v < 2).astype(np.int32)              # E/W-bound roads share phase 1
         self.dest = np.where(ids < 4 * v, ids % v, -1).astype(np.int32)
         self.nexts = np.array([self.get_next(i) for i in range(self.roads)], dtype=np.int32)
-        self.locs = self._segment_coordinates(0.02) * float(l)
         self.generate_entrypoints(0)
 
     def get_next(self, i):
@@ -46,30 +45,3 @@ class GridRoad(object):
                  3 * v + n * (m - 1) + np.arange(n)]
         keep = [s for k, s in enumerate(sides) if not (int(choices) >> k) & 1]
         self.entrypoints = (np.concatenate(keep) if keep else np.empty(0)).astype(np.int32)
-
-    def _segment_coordinates(self, eps):
-        """Start/end points of every road in grid units (only the renderer uses these)."""
-        v, n, m = self.intersections, self.n, self.m
-        locs = np.zeros((self.roads, 2, 2), dtype=np.float32)
-        for i in range(self.roads):
-            d, cell = divmod(i, v)
-            row, col = divmod(cell, n)
-            k = i - 4 * v
-            if d == 0:
-                seg = ((col - 1, row - eps), (col, row - eps))
-            elif d == 1:
-                seg = ((col + 1, row + eps), (col, row + eps))
-            elif d == 2:
-                seg = ((col + eps, row - 1), (col + eps, row))
-            elif d == 3:
-                seg = ((col - eps, row + 1), (col - eps, row))
-            elif k < n:
-                seg = ((k - eps, 0), (k - eps, -1))
-            elif k < n + m:
-                seg = ((n - 1, k - n - eps), (n, k - n - eps))
-            elif k < 2 * n + m:
-                seg = ((k - n - m + eps, m - 1), (k - n - m + eps, m))
-            else:
-                seg = ((0, k - 2 * n - m + eps), (-1, k - 2 * n - m + eps))
-            locs[i] = seg
-        return locs

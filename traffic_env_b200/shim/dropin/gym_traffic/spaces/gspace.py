@@ -3,11 +3,15 @@
 `limit`, typed by `limit`'s dtype.  Semantics preserved exactly - including that sample() draws from the GLOBAL
 numpy RNG with that dtype (action sequences of seeded runs depend on it) and that `contains` compares the array
 shape with the (list) shape as given."""
-import gym
 import numpy as np
 
+try:
+    from gym import Space as _Space
+except ImportError:      # EnvPool (traffic_env_b200/pool.py) loads this file by path and works without gym
+    _Space = object
 
-class GSpace(gym.Space):
+
+class GSpace(_Space):
     def __init__(self, shape, limit):
         self.shape, self.limit = shape, limit
         self.size = int(np.prod(shape))
