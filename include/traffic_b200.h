@@ -87,6 +87,8 @@ typedef struct te_stats {
   double disc_return_sum;    /* same with gamma^t weighting */
   uint64_t seq_fallback_ticks; /* env-ticks whose transfer phase ran in strict road order */
   uint64_t cars_exited;      /* cars that drove off an exit road (generated = live + exited + dropped) */
+  uint64_t arrival_saturations; /* Philox arrivals dropped because one entry road already had 255 arrivals in that tick
+                                   (must stay 0: te_create bounds the arrival rate far below; non-zero = misuse) */
 } te_stats;
 
 typedef struct te_handle te_handle;
@@ -96,11 +98,16 @@ typedef struct te_handle te_handle;
 void te_default_config(te_config *cfg);
 
 /* TrafficEnv.set_graph + seed_generator + reset_entrypoints (traffic_env.py:361-382, 250-253, 389-394)
-   for num_envs instances; uploads the topology tables of GridRoad (roadgraph.py:26-64). */
+   for num_envs instances; uploads the topology tables of GridRoad (roadgraph.py:26-64).  Rejects configurations
+   outside what parity is established for: non-finite or non-positive rate / length / v0 / a / b / delta / T, and
+   roads not longer than twice the farthest a car can travel in one tick. */
 int te_create(const te_config *cfg, te_handle **out);
 int te_destroy(te_handle *h);
 int te_get_dims(const te_handle *h, te_dims *out);
 const char *te_last_error(void);
+/* Number of CUDA devices the library can see (0 and an error when the driver is missing): lets callers and the
+   test-suite detect a GPU box without importing torch. */
+int te_device_count(int32_t *count);
 
 /* Topology tables as the device holds them (for tests): dest/nexts/phases int32[R], entry int32[num_entry]. */
 int te_get_topology(const te_handle *h, int32_t *dest, int32_t *nexts, int32_t *phases, int32_t *entry);
@@ -116,16 +123,34 @@ int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *init_phase, i
    tick of an env counts the ticks it has executed since te_create and is NOT rewound by reset (the
    reference never re-seeds its generator).  Ticks outside [first_tick, first_tick +
    horizon) have no arrivals; call again with a later window to stream a long schedule.
+   num_roads = length of roads[]; every offset must lie in [0, num_roads], each row non-decreasing, at most 255
+   arrivals per env tick, every road an entry road - otherwise the call fails and the old schedule stays.
    Buffers are copied; always host pointers. */
-int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t first_tick, int32_t horizon);
+int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t num_roads, int64_t first_tick,
+                    int32_t horizon);
 
 /* One actor step = Repeater(k_ticks)._step (+ Remi when TE_REMI) for every env (traffic_test.py:37-64).
    actions uint8[E, I] (non-zero = 1); obs float[E, 2r+I]; reward float[E, I]; done uint8[E].  The tick loop
    of an env stops after the tick that overflowed.  TE_DEVICE: one kernel launch on `stream`, asynchronous.
-   TE_HOST: synchronous; the batch is launched in slices and each finished slice's results are copied to the
-   host buffers while the next slices run (page-locked buffers, te_host_alloc, make those copies asynchronous). */
+   TE_HOST: synchronous; the batch is launched in slices; each finished slice's results travel to the host as compact
+   wire records (see te_step_wire) while the next slices run, and helper threads of the handle expand them into the
+   caller's arrays (TE_HOST_SLICES / TE_HOST_THREADS environment variables tune slices and threads). */
 int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
             int memspace, void *stream);
+
+/* The same actor step with its results as compact WIRE RECORDS, one per env (what te_step(TE_HOST) moves over PCIe
+   internally): u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done, `stride` bytes apart
+   (te_wire_layout) - 2.5 x fewer bytes than the float observation; the integer-valued observation entries
+   (passed <= 19 k_ticks, detected <= 18) travel as bytes, so k_ticks <= 13.  A consumer that feeds a policy can read the
+   records directly; te_expand_wire turns `count` records into te_step's float obs[count, 2r+I] / reward / done arrays
+   (host memory).  records: E * stride bytes, device memory (TE_DEVICE, asynchronous) or host memory (TE_HOST). */
+typedef struct te_wire_layout_t {
+  int32_t stride, passed, detected, light, reward, done; /* byte offsets inside one record */
+  int32_t max_k_ticks;
+} te_wire_layout_t;
+int te_wire_layout(const te_handle *h, te_wire_layout_t *out);
+int te_step_wire(te_handle *h, const uint8_t *actions, int32_t k_ticks, void *records, int memspace, void *stream);
+int te_expand_wire(const te_handle *h, const void *records, int32_t count, float *obs, float *reward, uint8_t *done);
 
 /* One physics tick = bare TrafficEnv._step (traffic_env.py:224-248): obs int32[E, 2r+2I]
    (passed | detected | current_phase | elapsed), reward float[E, I], done uint8[E]. */
@@ -160,6 +185,8 @@ int te_get_stats(te_handle *h, te_stats *out);
    order the reference appends them (tick, road index, pop order).  *count receives the number available;
    up to cap pairs are copied (either output may be NULL).  `clear` empties the device buffer afterwards. */
 int te_get_trip_times(te_handle *h, int32_t *env_out, float *trip_out, int64_t cap, int64_t *count, int clear);
+/* (returns 1, not an error, when more trips happened since the last clear than the device buffer - max(2^20, 64 E)
+   records - holds: the recorded ones are returned and `clear` is honoured; te_last_error() has the counts) */
 
 int te_synchronize(te_handle *h);
 

@@ -161,7 +161,7 @@ def test_full_wrapper_stack_and_launcher(dropin):
     assert list(single.unwrapped.current_phase) == [1] * 9          # a one-element action broadcasts, as in the reference
     assert np.isscalar(r) or np.ndim(r) == 0
     assert single.action_space.n == 9
-    from traffic_env_b200 import run
+    from tests.support import run_baselines as run
     for trainer in ("fixed", "greedy", "random", "const0", "const1"):
         mean = run.main(["--trainer", trainer, "--episodes", "2", "--episode_secs", "100"])
         assert np.isfinite(mean)

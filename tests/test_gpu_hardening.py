@@ -1,0 +1,220 @@
+"""GPU: round-2 hardening - trajectories with a non-default archetype (delta != 4; T and rate not powers of two: the
+longer arithmetic forms of te_math.cuh) against the oracle, a steady-state replay of sampled envs out of the full
+16384-env headline batch, a stress test aimed at the two hazards the kernel names (phase-C slot reuse -> ordered-transfer
+fallback; tick-stamped early break) on the 16/24/32-warp CTA variants, and the stricter argument checks of the C ABI."""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleEnv
+from tests.golden_util import live_walk
+from tests.test_gpu_fuzz_state import load_oracle, random_env_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("arch,rate,m,n,L,lcps", [
+    # x, v, l, a, delta, v0, b, T, s0, w
+    ([0.0, 9.5, 4.5, 2.2, 3.5, 15.3, 4.1, 1.7, 1.5, 0.0], 0.4, 3, 3, 250.0, 0.25),     # nothing a power of two, delta != 4
+    ([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 1.3, 1.0, 0.0], 0.3, 2, 3, 140.0, 0.4),   # delta == 4 but T, rate not powers of two
+    ([0.0, 12.0, 5.0, 1.5, 2.0, 17.0, 3.0, 2.0, 2.0, 0.0], 0.5, 4, 4, 200.0, 0.2),     # T, rate powers of two, delta != 4
+])
+def test_nondefault_archetype_trajectories(arch, rate, m, n, L, lcps):
+    from traffic_env_b200 import VecTrafficEnv
+    from traffic_env_b200.arrivals import gap_cdf
+    E, K, S = 24, 10, 45
+    arch = np.asarray(arch, np.float32)
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, rate=rate, arrivals="philox", seed=77, local_cars_per_sec=lcps,
+                        ticks_per_step=K, remi=True, archetype=arch)
+    rng = np.random.RandomState(5)
+    I = m * n
+    init = rng.randint(2, size=(E, I))
+    env.reset(init_phase=init)
+    cdf = gap_cdf(env.cars_per_sec * rate)
+    oracles = []
+    for e in range(E):
+        o = OracleEnv(m, n, L, rate)
+        o.set_archetype(arch)
+        o.reset(init[e])
+        o.philox_seed(77, e, cdf)
+        oracles.append(o)
+    cars = 0
+    for s in range(S):
+        if s % 4 == 0:
+            act = rng.randint(2, size=(E, I))
+        obs, rew, done = env.step(act)
+        for e, o in enumerate(oracles):
+            oo, orw, od = o.actor_step_philox(act[e], K, use_remi=True)
+            assert obs[e].tobytes() == oo.tobytes() and rew[e].tobytes() == orw.tobytes() and bool(done[e]) == od, (e, s)
+    st = env.get_state()
+    for e, o in enumerate(oracles):
+        assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all()
+        gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+        ox, ov = o.live_state()
+        assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), e
+        cars += len(ox)
+    assert cars > 20 * E, "the test is meant to have traffic on the map"
+    assert env.stats()["vehicle_updates"] == sum(o.vehicle_updates for o in oracles)
+    assert env.stats()["arrival_saturations"] == 0
+
+
+def test_headline_steady_state_replay_16384():
+    """The bench workload at full size, 300 actor steps into its ring-capacity-bound steady state (overflow in a third
+    of the steps, early breaks): 32 envs spread over the batch replayed from scratch on the oracle - every sampled
+    env's final ring indices, car state (bits), tick count and the last observation must match."""
+    from traffic_env_b200 import VecTrafficEnv
+    from traffic_env_b200.arrivals import gap_cdf
+    E, M, N, L, K, S = 16384, 10, 10, 500.0, 10, 300
+    env = VecTrafficEnv(m=M, n=N, length=L, num_envs=E, arrivals="philox", seed=2026, local_cars_per_sec=0.12,
+                        ticks_per_step=K, remi=True)
+    env.reset(init_phase=np.zeros((E, M * N), np.uint8))
+    ids = np.unique(np.concatenate([np.arange(0, E, 529), [1, E - 2, E - 1]]))[:32]
+    acts = np.zeros((S, len(ids), M * N), np.uint8)
+    last_obs = None
+    overflow_steps = 0
+    for s in range(S):
+        if s % 3 == 0:
+            a = env.greedy_actions().copy()
+        acts[s] = a[ids]
+        obs, rew, done = env.step(a)
+        overflow_steps += int(done[ids].sum())
+        last_obs = obs[ids].copy()
+    cdf = gap_cdf(env.cars_per_sec * 0.5)
+    assert overflow_steps > 100, "the steady state is meant to overflow often"
+    for j, e in enumerate(ids):
+        o = OracleEnv(M, N, L, 0.5)
+        o.reset(np.zeros(M * N, np.int32))
+        o.philox_seed(2026, int(e), cdf)
+        for s in range(S):
+            oo, orw, od = o.actor_step_philox(acts[s, j], K, use_remi=True)
+        st = env.get_state(int(e), 1)
+        assert (st["leading"][0] == o.leading).all() and (st["lastcar"][0] == o.lastcar).all(), e
+        gx, gv = live_walk(st["leading"][0], st["lastcar"][0], st["x"][0], st["v"][0])
+        ox, ov = o.live_state()
+        assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), e
+        assert float(st["steps"][0]) == float(o.steps), e
+        assert last_obs[j].tobytes() == oo.tobytes(), e
+        assert len(ox) > 2500
+    assert env.stats()["arrival_saturations"] == 0
+
+
+@pytest.mark.parametrize("m,n,L,E", [(10, 10, 60.0, 40), (13, 13, 60.0, 24), (15, 15, 60.0, 16)])
+def test_transfer_hazards_under_load(m, n, L, E):
+    """16-, 24- and 32-warp CTAs (512 / 768 / 1024-thread variants), many co-resident envs, short roads packed with cars
+    near the road end: most ticks pop two or more cars per road, so the parallel transfer phase keeps meeting the
+    slot-reuse hazard (-> strict-order fallback on that tick) and rings overflow (-> tick-stamped early break of the
+    fused step).  Fused K-tick steps against the oracle's tick loop; raw ticks are covered by test_gpu_fuzz_state."""
+    from traffic_env_b200 import VecTrafficEnv
+    rng = np.random.RandomState(31 * m + n)
+    K, S = 6, 4
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, arrivals="injected", remi=True, ticks_per_step=K)
+    R, r, I = env.roads, env.train_roads, env.intersections
+    states = [random_env_state(rng, R, r, I, L, True) for _ in range(E)]
+    T = K * S
+    scheds = [[list(rng.choice(env.entrypoints, size=rng.randint(0, 5))) for _ in range(T)] for _ in range(E)]
+    env.set_arrivals(scheds)
+    env.set_state({k: np.stack([s[k] for s in states]) for k in states[0]} | {"steps": np.zeros(E, np.float32)})
+    oracles = []
+    for e in range(E):
+        o = OracleEnv(m, n, L, 0.5)
+        load_oracle(o, states[e])
+        oracles.append(o)
+    cursor = np.zeros(E, np.int64)         # arrival-process tick of each env (advances by the ticks actually run)
+    multi_pop = breaks = 0
+    for s in range(S):
+        act = rng.randint(0, 2, size=(E, I))
+        obs, rew, done = env.step(act)
+        st = env.get_state()
+        for e, o in enumerate(oracles):
+            passed = np.zeros(r, np.float32)
+            od = False
+            for k in range(K):
+                before = o.leading.copy()
+                od = o.step(act[e], scheds[e][cursor[e]] if cursor[e] < T else [])
+                multi_pop += int((((o.leading - before) % 19) >= 2).sum())
+                cursor[e] += 1
+                passed += o.passed
+                if od:
+                    breaks += int(k < K - 1)
+                    break
+            orw = o.remi_reward().copy()
+            o.passed_dst[:] = 0
+            tag = "env %d step %d" % (e, s)
+            assert bool(done[e]) == od, tag
+            assert obs[e, :r].tobytes() == passed.tobytes(), tag + " passed"
+            assert (obs[e, r:2 * r] == o.detected).all(), tag + " detected"
+            assert rew[e].tobytes() == orw.tobytes(), tag + " reward"
+            assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all(), tag + " rings"
+            gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+            ox, ov = o.live_state()
+            assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), tag + " car state"
+    stats = env.stats()
+    assert multi_pop > 50 * E and breaks > 0
+    assert stats["seq_fallback_ticks"] > E, "the ordered-transfer fallback is meant to fire on most envs"
+    assert stats["overflows"] == sum(o.overflows for o in oracles)
+
+
+def test_strict_argument_checks():
+    from traffic_env_b200 import TrafficB200Error, VecTrafficEnv
+    env = VecTrafficEnv(m=3, n=3, num_envs=2, arrivals="injected")
+    H = 4
+    roads = np.array([0, 3, 6], np.int16)
+    ok = np.array([[0, 1, 1, 2, 3], [3, 3, 3, 3, 3]], np.int64)
+    env.set_arrivals_csr(ok, roads, H)
+    for bad, what in ((np.array([[0, 1, 1, 2, 4], [3, 3, 3, 3, 3]], np.int64), "beyond num_roads"),
+                      (np.array([[-1, 1, 1, 2, 3], [3, 3, 3, 3, 3]], np.int64), "outside"),
+                      (np.array([[0, 1, 1, 2, 3], [5, 5, 5, 5, 5]], np.int64), "outside|beyond"),
+                      (np.array([[0, 2, 1, 2, 3], [3, 3, 3, 3, 3]], np.int64), "not monotone")):
+        with pytest.raises(TrafficB200Error, match=what):
+            env.set_arrivals_csr(bad, roads, H)
+    obs, rew, done = env.step(np.zeros((2, 9)))     # the old (valid) schedule is still in place
+    assert env.stats()["cars_generated"] == 3
+    for kw, what in ((dict(length=10.0), "maximum displacement"), (dict(rate=0.0), "finite and positive"),
+                     (dict(length=float("nan")), "finite and positive"),
+                     (dict(archetype=[0, 11.11, 4, 3, 4, 0.0, 6, 2, 1, 0]), "v0"),
+                     (dict(archetype=[0, 11.11, 4, 3, 4, 13.89, float("inf"), 2, 1, 0]), "finite")):
+        with pytest.raises(TrafficB200Error, match=what):
+            VecTrafficEnv(m=2, n=2, num_envs=1, **kw)
+
+
+def test_wire_records_equal_float_outputs():
+    """The compact wire format of the host path: te_step_wire records (host and device memory) expand to exactly the
+    float obs / reward / done of te_step; steps of more than 13 ticks (passed counts no longer fit a byte) take the float
+    path and still agree with the device-buffer launch; remi off (overflow penalties of -10 n travel as f32)."""
+    import ctypes as C
+    import torch
+    from traffic_env_b200 import TrafficB200Error, VecTrafficEnv
+    from traffic_env_b200._lib import TE_DEVICE, check
+    E = 4096 + 11
+    kw = dict(m=3, n=3, length=250.0, num_envs=E, arrivals="philox", seed=5, local_cars_per_sec=0.6, ticks_per_step=10)
+    for remi in (True, False):
+        a, b, d = VecTrafficEnv(remi=remi, **kw), VecTrafficEnv(remi=remi, **kw), VecTrafficEnv(remi=remi, **kw)
+        rng = np.random.RandomState(8)
+        init = rng.randint(2, size=(E, 9))
+        for env in (a, b, d):
+            env.reset(init_phase=init)
+        dev = torch.device("cuda", 0)
+        d_rec = torch.zeros((E, a.wire.stride), dtype=torch.uint8, device=dev)
+        saw_done = False
+        for s in range(14):
+            act = rng.randint(2, size=(E, 9)).astype(np.uint8)
+            k = 14 if s == 9 else (3 if s == 5 else None)     # one step on the float path, one short step
+            obs, rew, done = a.step(act, k=k)
+            if k == 14:
+                with pytest.raises(TrafficB200Error, match="k_ticks"):
+                    b.step_wire(act, k=14)
+                o2, r2, d2 = b.step(act, k=14)
+                o2, r2, d2 = o2.copy(), r2.copy(), d2.copy()
+                d.step(act, k=14)
+            else:
+                rec = b.step_wire(act, k=k)
+                assert rec["passed"].dtype == np.uint8 and rec["light"].dtype == np.float32
+                assert (rec["passed"].astype(np.float32) == obs[:, :36]).all()
+                o2, r2, d2 = b.expand_wire()
+                check(d._L.te_step_wire(d._h, torch.from_numpy(act).to(dev).data_ptr(), d.ticks_per_step if k is None else k,
+                                        d_rec.data_ptr(), TE_DEVICE, None))
+                d.synchronize()
+                assert d_rec.cpu().numpy()[:, :a.wire.done + 1].tobytes() == b._wire_buf[:, :a.wire.done + 1].tobytes(), s
+            assert obs.tobytes() == o2.tobytes() and rew.tobytes() == r2.tobytes() and done.tobytes() == d2.tobytes(), s
+            saw_done = saw_done or bool(done.any())
+        assert saw_done, "the test is meant to include ring overflows"
+        assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] == d.stats()["vehicle_updates"]

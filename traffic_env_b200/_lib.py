@@ -15,8 +15,8 @@ TE_ARRIVALS_NONE, TE_ARRIVALS_INJECTED, TE_ARRIVALS_PHILOX = 0, 1, 2
 TE_PARAMS, TE_CAP = 10, 20
 
 EXPORTS = [
-    "te_default_config", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
-    "te_reset", "te_set_arrivals", "te_step", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
+    "te_default_config", "te_device_count", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
+    "te_reset", "te_set_arrivals", "te_step", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
     "te_greedy_actions", "te_get_state", "te_set_state", "te_get_stats", "te_get_trip_times",
     "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_fdiv_const_exhaustive", "te_test_philox",
 ]
@@ -42,8 +42,12 @@ class TeStats(C.Structure):
         ("ticks", C.c_uint64), ("actor_steps", C.c_uint64), ("vehicle_updates", C.c_uint64),
         ("overflows", C.c_uint64), ("cars_generated", C.c_uint64), ("episodes", C.c_uint64),
         ("return_sum", C.c_double), ("disc_return_sum", C.c_double), ("seq_fallback_ticks", C.c_uint64),
-        ("cars_exited", C.c_uint64),
+        ("cars_exited", C.c_uint64), ("arrival_saturations", C.c_uint64),
     ]
+
+
+class TeWireLayout(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("stride", "passed", "detected", "light", "reward", "done", "max_k_ticks")]
 
 
 class TrafficB200Error(RuntimeError):
@@ -72,9 +76,13 @@ def load():
     L.te_last_error.restype = C.c_char_p
     L.te_get_topology.argtypes = [vp, vp, vp, vp, vp]
     L.te_reset.argtypes = [vp, vp, vp, C.c_int, vp]
-    L.te_set_arrivals.argtypes = [vp, vp, vp, i64, i32]
+    L.te_set_arrivals.argtypes = [vp, vp, vp, i64, i64, i32]
+    L.te_device_count.argtypes = [C.POINTER(i32)]
     L.te_step.argtypes = [vp, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_raw.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.te_step_wire.argtypes = [vp, vp, i32, vp, C.c_int, vp]
+    L.te_wire_layout.argtypes = [vp, C.POINTER(TeWireLayout)]
+    L.te_expand_wire.argtypes = [vp, vp, i32, vp, vp, vp]
     L.te_remi_reward.argtypes = [vp, vp, C.c_int, vp]
     L.te_cars_on_roads.argtypes = [vp, vp, C.c_int, vp]
     L.te_greedy_actions.argtypes = [vp, vp, C.c_int, vp]
@@ -101,8 +109,20 @@ def load():
 
 
 def check(rc):
-    if rc != 0:
+    """C ABI convention: 0 = ok, < 0 = error (te_last_error has the text), > 0 = ok with a warning."""
+    if rc < 0:
         raise TrafficB200Error(load().te_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def device_count():
+    """CUDA devices visible to libtraffic_b200.so (0 when there is no driver / device); never raises."""
+    try:
+        n = C.c_int32(0)
+        load().te_device_count(C.byref(n))
+        return int(n.value)
+    except Exception:
+        return 0
 
 
 def default_config():

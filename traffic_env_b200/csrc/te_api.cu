@@ -10,7 +10,11 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/traffic_b200.h"
@@ -36,6 +40,84 @@ static int fail(const char *fmt, ...) {
     cudaError_t e_ = (call);                                                                  \
     if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// ---- host side of the wire format (te_kernels.cuh: wire_stride_bytes): expand compact env records into the caller's
+// float observation / reward / done arrays.  Plain loops (the compiler vectorises the byte -> float conversion); the
+// work is memory-bound and overlapped with the simulation of the following slices (ExpandPool).
+static void expand_records(const unsigned char *recs, int r, int I, int stride, long long n, float *obs, float *reward,
+                           uint8_t *done) {
+  const int ol = 2 * r + I;
+  for (long long e = 0; e < n; e++) {
+    const unsigned char *rec = recs + (size_t)e * stride;
+    float *o = obs + (size_t)e * ol;
+    for (int k = 0; k < 2 * r; k++) o[k] = (float)rec[k];
+    memcpy(o + 2 * r, rec + 2 * r, (size_t)I * 4);
+    memcpy(reward + (size_t)e * I, rec + 2 * r + 4 * I, (size_t)I * 4);
+    done[e] = rec[2 * r + 8 * I];
+  }
+}
+
+// A few helper threads per handle that wait for a slice's device-to-host copy (CUDA event) and expand it while the
+// GPU simulates the next slices.  Slices are dealt round-robin; the calling thread takes its share too.
+struct ExpandJob {
+  const unsigned char *recs; float *obs, *reward; uint8_t *done;
+  int r, I, stride, nslice, per, E;
+  cudaEvent_t *copied;
+};
+struct ExpandPool {
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  ExpandJob job;
+  unsigned long long generation = 0;
+  int pending = 0, device = 0, nthreads = 1;
+  bool stop = false;
+  std::atomic<int> failed{0};
+
+  void run_share(const ExpandJob &j, int tid) {
+    for (int k = tid; k < j.nslice; k += nthreads) {
+      if (cudaEventSynchronize(j.copied[k]) != cudaSuccess) { failed.store(1); continue; }
+      const int e0 = k * j.per, ne = std::min(j.per, j.E - e0);
+      if (ne <= 0) continue;
+      expand_records(j.recs + (size_t)e0 * j.stride, j.r, j.I, j.stride, ne, j.obs + (size_t)e0 * (2 * j.r + j.I),
+                     j.reward + (size_t)e0 * j.I, j.done + e0);
+    }
+  }
+  void start(int dev, int n) {
+    device = dev; nthreads = n < 1 ? 1 : n;
+    for (int t = 1; t < nthreads; t++)
+      workers.emplace_back([this, t]() {
+        cudaSetDevice(device);
+        unsigned long long seen = 0;
+        for (;;) {
+          ExpandJob j;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation; j = job;
+          }
+          run_share(j, t);
+          { std::lock_guard<std::mutex> lk(mu); if (--pending == 0) cv_done.notify_all(); }
+        }
+      });
+  }
+  // called by the stepping thread once every slice's kernel and copy have been queued
+  bool run(const ExpandJob &j) {
+    failed.store(0);
+    { std::lock_guard<std::mutex> lk(mu); job = j; pending = nthreads - 1; generation++; }
+    cv_go.notify_all();
+    run_share(j, 0);
+    { std::unique_lock<std::mutex> lk(mu); cv_done.wait(lk, [&] { return pending == 0; }); }
+    return failed.load() == 0;
+  }
+  void shutdown() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_go.notify_all();
+    for (std::thread &t : workers) t.join();
+    workers.clear();
+  }
+};
 
 struct te_handle {
   te_config cfg;
@@ -64,11 +146,17 @@ struct te_handle {
   float *w; TripRecord *d_trips; unsigned long long *d_trip_count; long long trip_cap;
   int warps;
   int smem_optin;
+  // wire path of the host API
+  unsigned char *d_wire, *h_wire;   // [E][wire_stride] device / page-locked host
+  int wire_stride, host_slices;
+  cudaEvent_t ev_copy[64];
+  ExpandPool *pool;
 };
 
 // One thread per (padded) road.  A kernel variant is compiled per row capacity MAXT >= Rp (its shared-memory layout
 // is a compile-time function of MAXT); the register cap follows from the CTA size and the number of CTAs an SM
-// should hold (1024 resident threads at 64 registers; 448 threads (10x10 grid) x 2 CTAs, shared-memory bound -> 72).
+// should hold: 1024 resident threads per SM at 64 registers wherever shared memory allows it (10x10 grid: 512 threads
+// x 2 CTAs, 101.7 KB each; 3x3 grid: 64 threads x 16 CTAs).
 typedef void (*step_kernel_t)(const StepParams);
 struct StepVariant { step_kernel_t fn; int maxt; };
 static StepVariant step_variant_for(int threads, bool validate) {
@@ -110,6 +198,15 @@ static void fill_idm(IdmConst &c, const float *a, float rate) {
 }
 
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
+
+extern "C" int te_device_count(int32_t *count) {
+  if (!count) return fail("te_device_count: null argument");
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  *count = (e == cudaSuccess) ? n : 0;
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail("te_device_count: %s", cudaGetErrorString(e)); }
+  return 0;
+}
 
 extern "C" void te_default_config(te_config *c) {
   memset(c, 0, sizeof(*c));
@@ -155,6 +252,10 @@ static std::vector<uint32_t> build_gap_cdf(double cars_per_tick) {
 static void free_handle(te_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->pool) { h->pool->shutdown(); delete h->pool; h->pool = nullptr; }
+  if (h->d_wire) cudaFree(h->d_wire);
+  if (h->h_wire) cudaFreeHost(h->h_wire);
+  for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   void *ptrs[] = {h->w, h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
                   h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
                   h->d_done, h->d_mask, h->d_init_phase, h->d_reward, h->d_obs_i /* d_obs_f aliases it */, h->d_cars,
@@ -181,6 +282,23 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (!cfg || !out) return fail("te_create: null argument");
   if (cfg->struct_size != (int32_t)sizeof(te_config)) return fail("te_create: te_config size mismatch (%d vs %zu)", cfg->struct_size, sizeof(te_config));
   if (cfg->m < 1 || cfg->n < 1 || cfg->num_envs < 1) return fail("te_create: bad dimensions");
+  {
+    // Physically sensible configurations only (bit-parity with the reference is established for these): finite
+    // positive tick length, road length, desired speed, acceleration and braking; and a road longer than twice the
+    // farthest a car can travel in one tick, so that a car handed to the next road cannot leave that road in the
+    // same tick (the reference's sequential road loop could pop it again; the parallel transfer phase does not).
+    const float *a = cfg->archetype;
+    auto pos = [](float f) { return std::isfinite(f) && f > 0.f; };
+    if (!pos(cfg->rate) || !pos(cfg->length)) return fail("te_create: rate and length must be finite and positive");
+    if (!pos(a[5]) || !pos(a[3]) || !pos(a[6]) || !pos(a[4]) || !pos(a[7]))
+      return fail("te_create: archetype v0, a, b, delta and T must be finite and positive");
+    for (int i = 0; i < TE_PARAMS; i++) if (!std::isfinite(a[i])) return fail("te_create: archetype[%d] is not finite", i);
+    if (a[1] < 0.f || a[2] < 0.f || a[8] < 0.f) return fail("te_create: archetype v, l and s0 must be non-negative");
+    const double vmax = std::max((double)a[5] + (double)a[3] * cfg->rate, (double)a[1]);
+    const double max_disp = cfg->rate * vmax + 0.5 * (double)a[3] * cfg->rate * cfg->rate;
+    if ((double)cfg->length <= 2.0 * max_disp)
+      return fail("te_create: road length %.3f is not above twice the maximum displacement per tick (%.3f)", cfg->length, max_disp);
+  }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -195,6 +313,8 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
   h->stream = h->stream2 = h->stream_copy = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = h->ev_copied = nullptr;
   for (cudaEvent_t &e : h->ev_slice) e = nullptr;
+  for (cudaEvent_t &e : h->ev_copy) e = nullptr;
+  h->d_wire = h->h_wire = nullptr; h->pool = nullptr; h->wire_stride = 0; h->host_slices = 1;
   h->timed = false; h->trip_cap = 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUH(cudaSetDevice(h->device));
@@ -243,6 +363,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
   CUH(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
   for (cudaEvent_t &e : h->ev_slice) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (cudaEvent_t &e : h->ev_copy) CUH(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUH(cudaEventCreate(&h->ev0)); CUH(cudaEventCreate(&h->ev1));
   CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -250,7 +371,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (cfg->flags & TE_VALIDATE) {
     CUH(dalloc(&h->w, E * h->Rp * CAP));
     CUH(cudaMemset(h->w, 0, E * h->Rp * CAP * sizeof(float)));
-    h->trip_cap = 1 << 20;
+    h->trip_cap = std::max<long long>(1ll << 20, 64ll * (long long)E);
     CUH(dalloc(&h->d_trips, (size_t)h->trip_cap)); CUH(dalloc(&h->d_trip_count, 1));
     CUH(cudaMemset(h->d_trip_count, 0, sizeof(unsigned long long)));
   }
@@ -263,6 +384,25 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(dalloc(&h->d_obs_i, E * (2 * h->r + 2 * h->I)));
   CUH(dalloc(&h->d_reward, E * h->I));
   h->d_obs_f = reinterpret_cast<float *>(h->d_obs_i);  // raw and fused observations are never live together
+  h->wire_stride = wire_stride_bytes(h->r, h->I);
+  CUH(dalloc(&h->d_wire, E * (size_t)h->wire_stride));
+  CUH(cudaHostAlloc((void **)&h->h_wire, E * (size_t)h->wire_stride, cudaHostAllocDefault));
+  {
+    // Host path: the batch is launched in slices (te_step, TE_HOST) and a few helper threads expand the compact
+    // records of finished slices into the caller's float arrays meanwhile.  TE_HOST_SLICES / TE_HOST_THREADS tune it.
+    int nslice = cfg->num_envs / 512;              // measured on the 16384-env workload: 4 / 8 / 16 / 32 / 64 slices
+    nslice = nslice < 1 ? 1 : (nslice > 32 ? 32 : nslice);  //   -> 1.10 / 1.16 / 1.20 / 1.22 / 1.17e11 vehicle-updates/s end to end
+    if (const char *ev = getenv("TE_HOST_SLICES")) { const int v = atoi(ev); if (v >= 1 && v <= 64) nslice = v; }
+    h->host_slices = nslice;
+    int nthr = 4;
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (hw && hw < 8) nthr = 2;
+    if ((size_t)cfg->num_envs * (size_t)(2 * h->r) < (1u << 20)) nthr = 1;   // small batches: not worth waking anybody
+    if (const char *ev = getenv("TE_HOST_THREADS")) { const int v = atoi(ev); if (v >= 1 && v <= 64) nthr = v; }
+    if (nthr > nslice) nthr = nslice;
+    h->pool = new ExpandPool();
+    h->pool->start(h->device, nthr);
+  }
   CUH(cudaMemcpy(h->d_nexts, nx.data(), nx.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_up, up.data(), up.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_entry_idx, eidx.data(), eidx.size(), cudaMemcpyHostToDevice));
@@ -346,6 +486,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
     CUH(cudaMemcpy(h->env, es.data(), E * sizeof(EnvScalars), cudaMemcpyHostToDevice));
   }
   CUH(cudaStreamSynchronize(h->stream));
+  CUH(cudaDeviceSynchronize());   // the blocking table / scalar uploads above are complete before any stream steps
 #undef CUH
   *out = h;
   return 0;
@@ -386,38 +527,49 @@ extern "C" int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *in
   return 0;
 }
 
-extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t first_tick,
-                               int32_t horizon) {
-  if (!h || !offsets || horizon < 0 || first_tick < 0) return fail("te_set_arrivals: bad argument");
+extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, int64_t num_roads,
+                               int64_t first_tick, int32_t horizon) {
+  if (!h || !offsets || horizon < 0 || first_tick < 0 || num_roads < 0) return fail("te_set_arrivals: bad argument");
+  if (num_roads > 0 && !roads) return fail("te_set_arrivals: roads is NULL but num_roads = %lld", (long long)num_roads);
   CU(cudaSetDevice(h->device));
   const size_t E = (size_t)h->cfg.num_envs, no = E * ((size_t)horizon + 1);
-  const int64_t total = offsets[no - 1];
-  for (size_t e = 0; e < E; e++)
-    for (int t = 0; t < horizon; t++)
-    {
-      const int64_t a0 = offsets[e * (horizon + 1) + t], a1 = offsets[e * (horizon + 1) + t + 1];
-      if (a0 > a1) return fail("te_set_arrivals: offsets not monotone");
+  // every range [off[e][t], off[e][t+1]) must lie inside roads[0 .. num_roads): the kernel indexes roads with them
+  for (size_t e = 0; e < E; e++) {
+    const int64_t *row = offsets + e * ((size_t)horizon + 1);
+    if (row[0] < 0 || row[0] > num_roads) return fail("te_set_arrivals: env %zu: offset %lld outside [0, %lld]", e, (long long)row[0], (long long)num_roads);
+    for (int t = 0; t < horizon; t++) {
+      const int64_t a0 = row[t], a1 = row[t + 1];
+      if (a0 > a1) return fail("te_set_arrivals: env %zu tick %d: offsets not monotone", e, t);
+      if (a1 > num_roads) return fail("te_set_arrivals: env %zu tick %d: offset %lld beyond num_roads %lld", e, t, (long long)a1, (long long)num_roads);
       if (a1 - a0 > 255) return fail("te_set_arrivals: more than 255 arrivals in one tick of one env");
     }
+  }
   std::vector<signed char> is_entry(h->R, 0);
   for (int rd : h->entry) is_entry[rd] = 1;
-  for (int64_t k = 0; k < total; k++)
+  for (int64_t k = 0; k < num_roads; k++)
     if (roads[k] < 0 || roads[k] >= h->R || !is_entry[roads[k]]) return fail("te_set_arrivals: road %d is not an entry road", (int)roads[k]);
-  CU(cudaStreamSynchronize(h->stream));
+  // steps may still be queued on caller-provided streams (TE_DEVICE) and read the old schedule
+  CU(cudaDeviceSynchronize());
   if (h->d_sched_off) { cudaFree(h->d_sched_off); h->d_sched_off = nullptr; }
   if (h->d_sched_roads) { cudaFree(h->d_sched_roads); h->d_sched_roads = nullptr; }
-  CU(dalloc(&h->d_sched_off, no)); CU(dalloc(&h->d_sched_roads, (size_t)(total > 0 ? total : 1)));
+  h->base.sched_off = nullptr; h->base.sched_roads = nullptr; h->base.horizon = 0;
+  CU(dalloc(&h->d_sched_off, no)); CU(dalloc(&h->d_sched_roads, (size_t)(num_roads > 0 ? num_roads : 1)));
   static_assert(sizeof(long long) == sizeof(int64_t), "int64");
-  CU(cudaMemcpy(h->d_sched_off, offsets, no * sizeof(int64_t), cudaMemcpyHostToDevice));
-  if (total > 0) CU(cudaMemcpy(h->d_sched_roads, roads, (size_t)total * sizeof(int16_t), cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(h->d_sched_off, offsets, no * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+  if (num_roads > 0) CU(cudaMemcpyAsync(h->d_sched_roads, roads, (size_t)num_roads * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaDeviceSynchronize());   // order the upload against every stream a later step may be launched on
   h->base.sched_off = h->d_sched_off; h->base.sched_roads = h->d_sched_roads; h->base.horizon = horizon;
   h->base.sched_first = first_tick;
   return 0;
 }
 
+// wire_only: the caller wants the compact records themselves (te_step_wire): `obs` is the record buffer
+// (device memory for TE_DEVICE; for TE_HOST the records land in the handle's page-locked buffer and `obs` receives them).
 static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, void *obs, float *reward, uint8_t *done,
-                       int memspace, void *stream) {
-  if (!h || !actions || !obs || !reward || !done) return fail("te_step: null argument");
+                       int memspace, void *stream, bool wire_only = false) {
+  if (!h || !actions || !obs || (!wire_only && (!reward || !done))) return fail("te_step: null argument");
+  if (wire_only && K > WIRE_MAX_K) return fail("te_step_wire: k_ticks must be <= %d (passed counts travel as bytes)", WIRE_MAX_K);
   if (K < 1 || K > MAX_K) return fail("te_step: k_ticks must be in [1, %d]", MAX_K);
   if (h->cfg.arrival_mode == TE_ARRIVALS_INJECTED && !h->base.sched_off) return fail("te_step: no arrival schedule set");
   CU(cudaSetDevice(h->device));
@@ -431,6 +583,7 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     p.actions = h->d_actions; p.obs_f = h->d_obs_f; p.obs_i = h->d_obs_i; p.reward = h->d_reward; p.done = h->d_done;
   } else {
     p.actions = actions; p.obs_f = (float *)obs; p.obs_i = (int *)obs; p.reward = reward; p.done = done;
+    if (wire_only) { p.wire = (unsigned char *)obs; p.wire_stride = h->wire_stride; }
   }
   if (!raw && (h->cfg.flags & TE_AUTO_RESET)) {
     te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, nullptr, nullptr, 1);
@@ -448,17 +601,20 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     return 0;
   }
   // Host buffers: the batch is launched in slices on two alternating streams (the tail of one slice overlaps the
-  // head of the next), and a third stream copies each finished slice's observations / rewards / done flags to the
-  // host while the following slices are simulated (envs are independent: any slicing gives the same results).
+  // head of the next), and a third stream copies each finished slice's results to the host while the following slices
+  // are simulated (envs are independent: any slicing gives the same results).  Fused steps of up to WIRE_MAX_K ticks
+  // travel as compact wire records (one copy per slice, 2.5 x fewer bytes than the float observation) that the
+  // handle's helper threads expand into the caller's arrays while the GPU works on the next slices.
   const int E_i = h->cfg.num_envs;
-  int nslice = E_i / 512;                            // measured on the 16384-env workload: 4 / 8 / 16 / 32 / 64 slices
-  nslice = nslice < 1 ? 1 : (nslice > 32 ? 32 : nslice);  //   -> 1.10 / 1.16 / 1.20 / 1.22 / 1.17e11 vehicle-updates/s end to end
-  if (const char *ev = getenv("TE_HOST_SLICES")) { const int v = atoi(ev); if (v >= 1 && v <= 64) nslice = v; }  // tuning knob
+  const int nslice = h->host_slices;
   const int per = (E_i + nslice - 1) / nslice;
+  const bool use_wire = !raw && K <= WIRE_MAX_K;
+  if (use_wire) { p.wire = h->d_wire; p.wire_stride = h->wire_stride; }
   CU(cudaEventRecord(h->ev_fork, st));               // actions (and the auto-reset) are complete on `st`
   CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   cudaStream_t lanes[2] = {st, h->stream2};
   const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;
+  int nk = 0;
   for (int k = 0, e0 = 0; e0 < E_i; k++, e0 += per) {
     const int ne = (E_i - e0) < per ? (E_i - e0) : per;
     cudaStream_t cs = lanes[k & 1];
@@ -467,11 +623,19 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_slice[k], cs));
     CU(cudaStreamWaitEvent(h->stream_copy, h->ev_slice[k], 0));
-    CU(cudaMemcpyAsync((char *)obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
-                       cudaMemcpyDeviceToHost, h->stream_copy));
-    CU(cudaMemcpyAsync(reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
-                       cudaMemcpyDeviceToHost, h->stream_copy));
-    CU(cudaMemcpyAsync(done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
+    if (use_wire) {
+      unsigned char *host_dst = wire_only ? (unsigned char *)obs : h->h_wire;
+      CU(cudaMemcpyAsync(host_dst + (size_t)e0 * h->wire_stride, h->d_wire + (size_t)e0 * h->wire_stride,
+                         (size_t)ne * h->wire_stride, cudaMemcpyDeviceToHost, h->stream_copy));
+      CU(cudaEventRecord(h->ev_copy[k], h->stream_copy));
+    } else {
+      CU(cudaMemcpyAsync((char *)obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
+                         cudaMemcpyDeviceToHost, h->stream_copy));
+      CU(cudaMemcpyAsync(reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
+                         cudaMemcpyDeviceToHost, h->stream_copy));
+      CU(cudaMemcpyAsync(done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
+    }
+    nk = k + 1;
   }
   CU(cudaEventRecord(h->ev_join, h->stream2));
   CU(cudaEventRecord(h->ev_copied, h->stream_copy));
@@ -479,6 +643,13 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
   CU(cudaStreamWaitEvent(st, h->ev_copied, 0));
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
+  if (use_wire && !wire_only) {
+    ExpandJob j = {h->h_wire, (float *)obs, reward, done, h->r, h->I, h->wire_stride, nk, per, E_i, h->ev_copy};
+    const bool ok = h->pool->run(j);
+    CU(cudaStreamSynchronize(st));
+    if (!ok) return fail("te_step: a device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
   CU(cudaStreamSynchronize(st));
   return 0;
 }
@@ -486,6 +657,23 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
 extern "C" int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
                        int memspace, void *stream) {
   return launch_step(h, actions, k_ticks, 0, obs, reward, done, memspace, stream);
+}
+
+extern "C" int te_step_wire(te_handle *h, const uint8_t *actions, int32_t k_ticks, void *records, int memspace, void *stream) {
+  return launch_step(h, actions, k_ticks, 0, records, nullptr, nullptr, memspace, stream, true);
+}
+
+extern "C" int te_wire_layout(const te_handle *h, te_wire_layout_t *out) {
+  if (!h || !out) return fail("te_wire_layout: null argument");
+  out->stride = h->wire_stride; out->passed = 0; out->detected = h->r; out->light = 2 * h->r;
+  out->reward = 2 * h->r + 4 * h->I; out->done = 2 * h->r + 8 * h->I; out->max_k_ticks = WIRE_MAX_K;
+  return 0;
+}
+
+extern "C" int te_expand_wire(const te_handle *h, const void *records, int32_t count, float *obs, float *reward, uint8_t *done) {
+  if (!h || !records || !obs || !reward || !done || count < 0) return fail("te_expand_wire: bad argument");
+  expand_records((const unsigned char *)records, h->r, h->I, h->wire_stride, count, obs, reward, done);
+  return 0;
 }
 
 extern "C" int te_step_raw(te_handle *h, const uint8_t *actions, int32_t *obs, float *reward, uint8_t *done,
@@ -618,12 +806,16 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
     }
     if (steps) hes[e].steps = steps[e];
   }
-  CU(cudaMemcpy(h->x + env_begin * row, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->v + env_begin * row, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->elapsed + (size_t)env_begin * I, hel.data(), hel.size() * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->phase + (size_t)env_begin * I, hph.data(), hph.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->passed_dst + (size_t)env_begin * I, hpd.data(), hpd.size(), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(h->env + env_begin, hes.data(), hes.size() * sizeof(EnvScalars), cudaMemcpyHostToDevice));
+  // uploads go through the handle's stream and the device is synchronised afterwards, so they are ordered against
+  // steps on ANY stream (the step streams are non-blocking: the legacy default stream does not order against them)
+  CU(cudaMemcpyAsync(h->x + env_begin * row, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->v + env_begin * row, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->elapsed + (size_t)env_begin * I, hel.data(), hel.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->phase + (size_t)env_begin * I, hph.data(), hph.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->passed_dst + (size_t)env_begin * I, hpd.data(), hpd.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->env + env_begin, hes.data(), hes.size() * sizeof(EnvScalars), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -636,6 +828,7 @@ extern "C" int te_get_stats(te_handle *h, te_stats *out) {
   out->ticks = s.ticks; out->actor_steps = s.actor_steps; out->vehicle_updates = s.vehicle_updates;
   out->overflows = s.overflows; out->cars_generated = s.cars_generated; out->episodes = s.episodes;
   out->return_sum = s.return_sum; out->disc_return_sum = s.disc_return_sum; out->seq_fallback_ticks = s.seq_fallback_ticks; out->cars_exited = s.cars_exited;
+  out->arrival_saturations = s.arrival_saturations;
   return 0;
 }
 
@@ -646,18 +839,26 @@ extern "C" int te_get_trip_times(te_handle *h, int32_t *env_out, float *trip_out
   CU(cudaDeviceSynchronize());
   unsigned long long n = 0;
   CU(cudaMemcpy(&n, h->d_trip_count, sizeof(n), cudaMemcpyDeviceToHost));
-  if ((long long)n > h->trip_cap) return fail("te_get_trip_times: %llu trips recorded but the buffer holds %lld; read more often", n, h->trip_cap);
-  *count = (int64_t)n;
-  if (n && (env_out || trip_out)) {
-    std::vector<TripRecord> recs(n);
-    CU(cudaMemcpy(recs.data(), h->d_trips, n * sizeof(TripRecord), cudaMemcpyDeviceToHost));
+  // The device counts every trip but records only the first trip_cap of them: on overflow the recorded ones are still
+  // returned (and cleared when asked), and the call reports the truncation with return code 1.
+  const bool truncated = (long long)n > h->trip_cap;
+  const unsigned long long have = truncated ? (unsigned long long)h->trip_cap : n;
+  *count = (int64_t)have;
+  if (have && (env_out || trip_out)) {
+    std::vector<TripRecord> recs(have);
+    CU(cudaMemcpy(recs.data(), h->d_trips, have * sizeof(TripRecord), cudaMemcpyDeviceToHost));
     // the reference appends in (env-local) tick order, road-index order, pop order
     std::sort(recs.begin(), recs.end(), [](const TripRecord &a, const TripRecord &b) {
       return a.env != b.env ? a.env < b.env : a.order < b.order; });
-    const int64_t m = (int64_t)n < cap ? (int64_t)n : cap;
+    const int64_t m = (int64_t)have < cap ? (int64_t)have : cap;
     for (int64_t i = 0; i < m; i++) { if (env_out) env_out[i] = recs[i].env; if (trip_out) trip_out[i] = recs[i].trip; }
   }
   if (clear) CU(cudaMemset(h->d_trip_count, 0, sizeof(unsigned long long)));
+  if (truncated) {
+    g_err = "te_get_trip_times: " + std::to_string(n) + " trips since the last clear but the buffer holds " +
+            std::to_string(h->trip_cap) + "; the first ones were returned, read more often";
+    return 1;
+  }
   return 0;
 }
 

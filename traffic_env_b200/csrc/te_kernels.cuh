@@ -57,7 +57,7 @@ struct EnvScalars {
 
 struct DeviceStats {
   unsigned long long ticks, actor_steps, vehicle_updates, overflows, cars_generated, episodes, seq_fallback_ticks,
-      cars_exited;
+      cars_exited, arrival_saturations;
   double return_sum, disc_return_sum;
 };
 
@@ -98,6 +98,10 @@ struct StepParams {
   int *obs_i;                   // [E][2r+2I]  (raw tick)
   float *reward;                // [E][I]
   uint8_t *done;                // [E]
+  // compact wire record per env (te_step with host buffers / te_step_wire) instead of obs_f / reward / done:
+  //   u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done | pad   (wire_stride bytes, see wire_layout)
+  unsigned char *wire;
+  int wire_stride;
   // arrivals
   const long long *sched_off;   // [E*(horizon+1)]
   const short *sched_roads;
@@ -108,6 +112,12 @@ struct StepParams {
   uint32_t seed;
   long long env_id_base;
 };
+
+// Wire record of one env actor step: everything te_step returns, in 1/2.5 of the bytes of the float observation
+// (passed <= 19 K and detected <= 18 fit a byte for K <= 13 ticks).  Offsets: passed 0, detected r, light 2r
+// (4-byte aligned: r = 4 V), reward 2r + 4I, done 2r + 8I; stride rounded up to 16 bytes.
+__host__ __device__ constexpr int wire_stride_bytes(int r, int I) { return (2 * r + 8 * I + 1 + 15) / 16 * 16; }
+constexpr int WIRE_MAX_K = 13;     // 13 * 19 = 247 <= 255
 
 // HBM row header: x[road][0] bits = leading | lastcar << 8 | detected << 16, v[road][0] bits = waiting.
 __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int detected) {
@@ -349,8 +359,18 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         long long before = __shfl_up_sync(FULL, tick, 1);
         if (lane == 0) before = prev;
         if (tick < p.K) {
+          // 8-bit count per (tick, entry road), four to a word; bumped with a CAS so that a 256th arrival saturates
+          // (and is reported through te_stats.arrival_saturations) instead of carrying into the neighbouring count
           const int idx = (int)__umulhi(o[1], (uint32_t)p.n_entry) + (int)tick * p.n_entry;
-          atomicAdd(reinterpret_cast<unsigned int *>(s.cnt) + (idx >> 2), 1u << ((idx & 3) * 8));
+          unsigned int *wp = reinterpret_cast<unsigned int *>(s.cnt) + (idx >> 2);
+          const int sh = (idx & 3) * 8;
+          unsigned int seen = *wp;
+          for (;;) {
+            if (((seen >> sh) & 0xffu) == 0xffu) { atomicAdd(&p.stats->arrival_saturations, 1ull); break; }
+            const unsigned int prev = atomicCAS(wp, seen, seen + (1u << sh));
+            if (prev == seen) break;
+            seen = prev;
+          }
         }
         // after T ticks, for before < T <= tick (and T <= K), my draw is the next car: skip = tick - T
         for (long long T = (before + 1 > 1 ? before + 1 : 1); T <= tick && T <= p.K; T++) {
@@ -610,6 +630,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
 
   const int obs_f_len = 2 * p.r + p.I, obs_i_len = 2 * p.r + 2 * p.I;
   const bool clear_remi = !p.raw && (p.flags & F_REMI);
+  unsigned char *wire_rec = (!p.raw && p.wire) ? p.wire + (size_t)env * p.wire_stride : nullptr;
   // final light state after `ticks_run` ticks, reward
   for (int i = tid; i < p.I; i += blockDim.x) {
     const bool ls_act = learn_switch && s.act[i];
@@ -630,15 +651,21 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         else if (pd && green && !w) rew = __fadd_rn(rew, 0.5f);
       }
     }
-    p.reward[(size_t)env * p.I + i] = rew;
     p.passed_dst[(size_t)env * p.I + i] = clear_remi ? 0 : s.pdst[i];
     if (p.raw) {
+      p.reward[(size_t)env * p.I + i] = rew;
       p.obs_i[(size_t)env * obs_i_len + 2 * p.r + i] = ph_f;
       p.obs_i[(size_t)env * obs_i_len + 2 * p.r + p.I + i] = el_f;
     } else {
       // Repeater: obs[-I:] / 100 * (2 * phase - 1): int32 / int -> float64, cast to float32 on store
-      p.obs_f[(size_t)env * obs_f_len + 2 * p.r + i] =
-          __double2float_rn(__dmul_rn(__ddiv_rn((double)el_f, 100.0), (double)(2 * ph_f - 1)));
+      const float light = __double2float_rn(__dmul_rn(__ddiv_rn((double)el_f, 100.0), (double)(2 * ph_f - 1)));
+      if (wire_rec) {
+        reinterpret_cast<float *>(wire_rec + 2 * p.r)[i] = light;
+        reinterpret_cast<float *>(wire_rec + 2 * p.r + 4 * p.I)[i] = rew;
+      } else {
+        p.reward[(size_t)env * p.I + i] = rew;
+        p.obs_f[(size_t)env * obs_f_len + 2 * p.r + i] = light;
+      }
     }
     s.ovf[i] = __float_as_int(rew);  // reuse: reward for the return statistic below
   }
@@ -646,6 +673,9 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (p.raw) {
       p.obs_i[(size_t)env * obs_i_len + my_road] = passed;
       p.obs_i[(size_t)env * obs_i_len + p.r + my_road] = det;
+    } else if (wire_rec) {
+      wire_rec[my_road] = (unsigned char)passed;
+      wire_rec[p.r + my_road] = (unsigned char)det;
     } else {
       p.obs_f[(size_t)env * obs_f_len + my_road] = (float)passed;
       p.obs_f[(size_t)env * obs_f_len + p.r + my_road] = (float)det;
@@ -664,7 +694,8 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   }
   if (tid == 0) {
     const bool overflowed = s.misc[0] != 0x7fffffff;
-    p.done[env] = overflowed ? 1 : 0;
+    if (wire_rec) wire_rec[2 * p.r + 8 * p.I] = overflowed ? 1 : 0;
+    else p.done[env] = overflowed ? 1 : 0;
     es->steps = es->steps + (float)ticks_run;
     es->sched_cursor += ticks_run;
     if (p.arrival_mode == ARR_PHILOX) { es->ph_draw = s.snap[2 * ticks_run]; es->ph_skip = s.snap[2 * ticks_run + 1]; }

@@ -74,6 +74,10 @@ class VecTrafficEnv(object):
         self.ticks_per_step = int(ticks_per_step)
         self.device = int(device)
         self.remi = bool(remi)
+        self.auto_reset = bool(auto_reset)
+        wl = _lib.TeWireLayout()
+        check(L.te_wire_layout(self._h, C.byref(wl)))
+        self.wire = wl
         self.dest = np.empty(self.roads, np.int32)
         self.nexts = np.empty(self.roads, np.int32)
         self.phases = np.empty(self.roads, np.int32)
@@ -89,6 +93,7 @@ class VecTrafficEnv(object):
         self._done = self._host_array((E,), np.uint8)
         self._act = self._host_array((E, I), np.uint8)
         self._cars = self._host_array((E, self.roads), np.int32)
+        self._wire_buf = None   # page-locked record buffer, allocated on first step_wire()
 
     def _host_array(self, shape, dtype):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -102,7 +107,7 @@ class VecTrafficEnv(object):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.te_destroy(self._h)
             self._h = C.c_void_p()
-            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars"):
+            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars", "_wire_buf"):
                 setattr(self, name, None)
             for ptr in self._pinned:
                 self._L.te_host_free(ptr)
@@ -116,10 +121,13 @@ class VecTrafficEnv(object):
 
     # ------------------------------------------------------------ helpers
     def _actions(self, actions):
+        """Any array-like of truthy values (bool from A3C, int32 from DQN, float64 from `fixed`, ...) -> the page-locked
+        uint8 action buffer.  Bytes are copied as they are: the device tests `!= 0` itself."""
         a = np.asarray(actions)
-        if a.dtype != np.bool_ and a.dtype != np.uint8:
-            a = a.astype(bool)
-        np.not_equal(a.reshape(self.num_envs, self.intersections), 0, out=self._act.view(np.bool_))
+        if a.dtype == np.bool_ or a.dtype == np.uint8:
+            np.copyto(self._act.view(a.dtype), a.reshape(self.num_envs, self.intersections))
+        else:
+            np.not_equal(a.reshape(self.num_envs, self.intersections), 0, out=self._act.view(np.bool_))
         return self._act
 
     # ------------------------------------------------------------ reference API, batched
@@ -152,9 +160,11 @@ class VecTrafficEnv(object):
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         roads = np.ascontiguousarray(roads, dtype=np.int16)
         assert offsets.size == self.num_envs * (horizon + 1)
+        nroads = roads.size
         if roads.size == 0:
             roads = np.zeros(1, np.int16)
-        check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(first_tick), int(horizon)))
+        check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(nroads), int(first_tick),
+                                      int(horizon)))
 
     def step(self, actions, k=None):
         """One actor step (Repeater(k) [+ Remi]) for every env; returns (obs, reward, done) host arrays
@@ -164,6 +174,42 @@ class VecTrafficEnv(object):
         check(self._L.te_step(self._h, a.ctypes.data, k, self._obs.ctypes.data, self._reward.ctypes.data,
                               self._done.ctypes.data, TE_HOST, None))
         return self._obs, self._reward, self._done
+
+    def step_wire(self, actions, k=None):
+        """step() with the results left in the compact wire format (te_step_wire): a dict of views into one page-locked
+        record buffer - passed u8[E, r], detected u8[E, r], light f32[E, I], reward f32[E, I], done u8[E] - for consumers
+        that feed a policy directly; `expand_wire()` gives the float arrays of step()."""
+        a = self._actions(actions)
+        k = self.ticks_per_step if k is None else int(k)
+        E, r, I, wl = self.num_envs, self.train_roads, self.intersections, self.wire
+        if self._wire_buf is None:
+            self._wire_buf = self._host_array((E, wl.stride), np.uint8)
+        check(self._L.te_step_wire(self._h, a.ctypes.data, k, self._wire_buf.ctypes.data, TE_HOST, None))
+        w = self._wire_buf
+        return {"passed": w[:, wl.passed:wl.passed + r], "detected": w[:, wl.detected:wl.detected + r],
+                "light": w[:, wl.light:wl.light + 4 * I].view(np.float32),
+                "reward": w[:, wl.reward:wl.reward + 4 * I].view(np.float32), "done": w[:, wl.done]}
+
+    def expand_wire(self, env_begin=0, count=None):
+        """Float (obs, reward, done) of step() from the records of the last step_wire()."""
+        count = self.num_envs - env_begin if count is None else count
+        rec = self._wire_buf[env_begin:env_begin + count]
+        obs, rew, done = self._obs[env_begin:env_begin + count], self._reward[env_begin:env_begin + count], self._done[env_begin:env_begin + count]
+        check(self._L.te_expand_wire(self._h, rec.ctypes.data, count, obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+        return obs, rew, done
+
+    def d2h_bytes_per_step(self, k=None):
+        """Bytes te_step(TE_HOST) moves device -> host per actor step."""
+        k = self.ticks_per_step if k is None else int(k)
+        E = self.num_envs
+        if k <= self.wire.max_k_ticks:
+            return E * self.wire.stride
+        return E * (self.obs_len * 4 + self.intersections * 4 + 1)
+
+    def host_path_note(self):
+        return ("compact wire records of %d B per env (u8 passed / detected, f32 light / reward, u8 done) expanded on the "
+                "host into float obs[%d] / reward[%d] / done by the handle's helper threads" %
+                (self.wire.stride, self.obs_len, self.intersections))
 
     def step_raw(self, actions):
         """One physics tick (bare TrafficEnv._step); obs is int32 passed|detected|phase|elapsed."""
@@ -230,7 +276,10 @@ class VecTrafficEnv(object):
         check(self._L.te_get_trip_times(self._h, None, None, 0, C.byref(n), 0))
         envs = np.empty(n.value, np.int32)
         trips = np.empty(n.value, np.float32)
-        check(self._L.te_get_trip_times(self._h, envs.ctypes.data, trips.ctypes.data, n.value, C.byref(n), int(clear)))
+        rc = check(self._L.te_get_trip_times(self._h, envs.ctypes.data, trips.ctypes.data, n.value, C.byref(n), int(clear)))
+        if rc > 0:
+            import warnings
+            warnings.warn(self._L.te_last_error().decode("utf-8", "replace"))
         return envs, trips
 
     def stats(self):
