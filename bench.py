@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="one launch per actor step + a separate greedy-controller "
+                    "kernel every `spacing` steps (round-1 scheme) instead of te_step_multi")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -214,6 +216,7 @@ def bench_config(a, w, envs):
             "envs_per_gpu": envs, "policy": "greedy(spacing=%d)" % SPACING, "ticks_per_actor_step": K_TICKS,
             "arrivals": "philox, local_cars_per_sec=%.2f (reference default)" % w["lcps"],
             "wrappers": "Remi(Repeater(10))",
+            "launches": "te_step_multi: the %d actor steps a greedy decision holds for are one launch, controller in the kernel" % SPACING,
             "reset": "none (env keeps stepping after overflow, as the bare reference env does); pre-rolled into the "
                      "ring-capacity-bound steady state: ~48 % mean ring occupancy, NOT near-full in the mean (DESIGN.md 7); "
                      "the auto-reset variant is secondary.headline_auto_reset",
@@ -296,19 +299,23 @@ def allreduce(c, vals, op="sum"):
 class Runner(object):
     """One batched env on this rank plus its device-resident and host-side step loops."""
 
-    def __init__(self, c, w, E, policy="greedy", auto_reset=False, episode_len=0):
+    def __init__(self, c, w, E, policy="greedy", auto_reset=False, episode_len=0, multi=True):
         from traffic_env_b200 import VecTrafficEnv
         torch = c.torch
         self.c, self.w, self.E, self.policy = c, w, E, policy
+        # greedy decisions hold for `spacing` actor steps (greedy.py:14-16): those steps are ONE te_step_multi launch with
+        # the controller evaluated in the kernel (not for TE_AUTO_RESET handles, which reset between te_step calls)
+        self.multi = bool(multi) and policy == "greedy" and not auto_reset
         self.env = VecTrafficEnv(m=w["m"], n=w["n"], length=w["length"], num_envs=E, local_cars_per_sec=w["lcps"],
                                  arrivals="philox", seed=2026, env_id_base=c.rank * E, device=c.local,
                                  ticks_per_step=K_TICKS, remi=True, auto_reset=auto_reset, episode_len=episode_len)
         env = self.env
         self.I, self.OL = env.intersections, env.obs_len
         self.d_act = torch.zeros((E, self.I), dtype=torch.uint8, device=c.dev)
-        self.d_obs = torch.empty((E, self.OL), dtype=torch.float32, device=c.dev)
-        self.d_rew = torch.empty((E, self.I), dtype=torch.float32, device=c.dev)
-        self.d_done = torch.empty((E,), dtype=torch.uint8, device=c.dev)
+        ns = SPACING if self.multi else 1
+        self.d_obs = torch.empty((ns, E, self.OL), dtype=torch.float32, device=c.dev)
+        self.d_rew = torch.empty((ns, E, self.I), dtype=torch.float32, device=c.dev)
+        self.d_done = torch.empty((ns, E), dtype=torch.uint8, device=c.dev)
         self.launches = 0
         self.h_act = np.zeros((E, self.I), dtype=np.uint8)
         if policy == "random":
@@ -318,6 +325,37 @@ class Runner(object):
         env.reset()
         torch.cuda.synchronize()
 
+    def device_steps(self, n, s0=0):
+        """n actor steps of every env, device-resident; returns nothing (asynchronous)."""
+        if not self.multi:
+            for s in range(s0, s0 + n):
+                self.device_step(s)
+            return
+        s = s0
+        while s < s0 + n:
+            k = min(SPACING - s % SPACING, s0 + n - s)    # up to the next controller decision
+            self.env.step_multi_device(k, self.d_act, self.d_obs, self.d_rew, self.d_done, controller="greedy" if s % SPACING == 0 else "given",
+                                       stream=self.c.stream)
+            self.launches += 1
+            s += k
+
+    def host_steps(self, n, s0=0):
+        if not self.multi:
+            acc = 0.0
+            for s in range(s0, s0 + n):
+                acc += self.host_step(s)
+            return acc
+        s, acc = s0, 0.0
+        while s < s0 + n:
+            k = min(SPACING - s % SPACING, s0 + n - s)
+            act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given")
+            if s % SPACING == 0:
+                self.h_act[:] = act
+            for j in range(k):
+                acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])   # every actor step's result is read on the host
+            s += k
+        return acc
+
     def device_step(self, s):
         if self.policy == "greedy":
             if s % SPACING == 0:
@@ -326,7 +364,7 @@ class Runner(object):
             act = self.d_act
         else:
             act = self.d_rand[s % 8]
-        self.env.step_device(act, self.d_obs, self.d_rew, self.d_done, stream=self.c.stream)
+        self.env.step_device(act, self.d_obs[0], self.d_rew[0], self.d_done[0], stream=self.c.stream)
         self.launches += 1 + (1 if self.env_auto_reset else 0)
 
     @property
@@ -348,16 +386,14 @@ class Runner(object):
     def timed_device(self, steps, warmup):
         c, env = self.c, self.env
         with c.torch.cuda.stream(c.tstream):
-            for s in range(warmup):
-                self.device_step(s)
+            self.device_steps(warmup)
             barrier(c)
             st0 = env.stats()
             self.launches = 0
             ev0, ev1 = c.torch.cuda.Event(enable_timing=True), c.torch.cuda.Event(enable_timing=True)
             barrier(c)
             ev0.record(c.tstream)
-            for s in range(steps):
-                self.device_step(s)
+            self.device_steps(steps)
             ev1.record(c.tstream)
             barrier(c)
         ms = ev0.elapsed_time(ev1)
@@ -371,13 +407,11 @@ class Runner(object):
 
     def timed_host(self, steps, warmup):
         c, env = self.c, self.env
-        for s in range(warmup):
-            self.host_step(s)
+        self.host_steps(warmup)
         barrier(c)
         b0 = env.stats()["vehicle_updates"]
         t0 = time.perf_counter()
-        for s in range(steps):
-            self.host_step(s)
+        self.host_steps(steps)
         c.torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         vu = allreduce(c, [env.stats()["vehicle_updates"] - b0])[0]
@@ -385,14 +419,17 @@ class Runner(object):
         E, I, OL = self.E, self.I, self.OL
         return {"value": vu / t, "unit": "vehicle-updates/s", "h2d_bytes_per_step": int(E * I),
                 "d2h_bytes_per_step": int(env.d2h_bytes_per_step() + (E * I // SPACING if self.policy == "greedy" else 0)),
-                "steps": steps}
+                "steps": steps, "host_calls_per_step": (1.0 / SPACING) if self.multi else (1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0))}
 
     def kernel_times(self, n):
+        """Mean duration of one step-kernel launch (CUDA events on the launch stream, te_last_kernel_ms) and the
+        vehicle-updates it processed; a launch is `steps_per_launch` actor steps."""
         kms, kvu = [], []
+        spl = SPACING if self.multi else 1
         with self.c.torch.cuda.stream(self.c.tstream):
-            for s in range(n):
+            for i in range(n):
                 b0 = self.env.stats()["vehicle_updates"]
-                self.device_step(s)
+                self.device_steps(spl, i * spl)
                 kms.append(self.env.last_kernel_ms())
                 kvu.append(self.env.stats()["vehicle_updates"] - b0)
         return float(np.mean(kms)), float(np.mean(kvu))
@@ -517,10 +554,9 @@ def secondary_block(c, a, arith_peak):
                           "what": "4 envs of each rank's 131072-env default-grid batch vs the CPU oracle (same Philox key): "
                                   "actions, obs, reward, done every step and the final car state, bit for bit; min over ranks"}
     # (i) default grid, 131072 envs per GPU: greedy / no reset (kernel-quality number, comparable across rounds) ...
-    r3 = Runner(c, w3, E3, policy="greedy")
+    r3 = Runner(c, w3, E3, policy="greedy", multi=not a.no_multi)
     with c.torch.cuda.stream(c.tstream):
-        for s in range(w3["preroll"]):
-            r3.device_step(s)
+        r3.device_steps(w3["preroll"])
     d = r3.timed_device(steps, warm)
     k_ms, k_vu = r3.kernel_times(min(steps, 8))
     e2e = r3.timed_host(max(3, steps // 2), 3)
@@ -536,8 +572,7 @@ def secondary_block(c, a, arith_peak):
     # ... and as BASELINE config 4 prescribes: random policy, auto-reset (overflow or 120 actor steps)
     r4 = Runner(c, w3, E3, policy="random", auto_reset=True, episode_len=EPISODE_LEN)
     with c.torch.cuda.stream(c.tstream):
-        for s in range(EPISODE_LEN + 17):     # past the first synchronous episode boundary
-            r4.device_step(s)
+        r4.device_steps(EPISODE_LEN + 17)     # past the first synchronous episode boundary
     d = r4.timed_device(steps, warm)
     e2e = r4.timed_host(max(3, steps // 2), 3)
     occ = r4.occupancy()
@@ -555,8 +590,7 @@ def secondary_block(c, a, arith_peak):
     Eh = a.envs or wh["envs"]
     rh = Runner(c, wh, Eh, policy="greedy", auto_reset=True, episode_len=EPISODE_LEN)
     with c.torch.cuda.stream(c.tstream):
-        for s in range(EPISODE_LEN + 40):
-            rh.device_step(s)
+        rh.device_steps(EPISODE_LEN + 40)
     d = rh.timed_device(steps, warm)
     occ = rh.occupancy()
     out["headline_auto_reset"] = {
@@ -596,7 +630,7 @@ def b200_arm(a):
     w = WORKLOADS[a.workload]
     E = a.envs or w["envs"]
     preroll = w["preroll"] if a.preroll < 0 else a.preroll
-    run = Runner(c, w, E, policy="greedy")
+    run = Runner(c, w, E, policy="greedy", multi=not a.no_multi)
     env = run.env
     I, OL = run.I, run.OL
     sampler = ClockSampler(c.local)
@@ -604,8 +638,7 @@ def b200_arm(a):
         sampler.start()   # nvidia-smi needs a few hundred ms to deliver its first sample; the pre-roll, the warm-up
                           # and the timed region run the same kernel back to back, so all samples are under load
     with torch.cuda.stream(c.tstream):
-        for s in range(preroll):
-            run.device_step(s)
+        run.device_steps(preroll)
     torch.cuda.synchronize()
     occ = run.occupancy()
     d = run.timed_device(a.steps, a.warmup)
@@ -616,10 +649,13 @@ def b200_arm(a):
 
     # per-launch kernel time (CUDA events on the launch stream, separate pass so the sync does not sit in the timed region)
     k_ms, k_vu = run.kernel_times(min(a.steps, 10))
-    cars_env = k_vu / E / (loc["ticks"] / max(loc["actor_steps"], 1))
+    spl = SPACING if run.multi else 1                      # actor steps per launch
+    cars_env = k_vu / E / spl / (loc["ticks"] / max(loc["actor_steps"], 1))
     R, r = env.roads, env.train_roads
     arr_per_step = loc["cars_generated"] / max(loc["actor_steps"], 1)
-    bytes_env = 2 * (8 * cars_env + 8 * R) + 4 * I + 4 * (2 * r + I) + 4 * I + 2 * 8 * I + 1 + 2 * arr_per_step
+    # SURVEY.md 8d per env and LAUNCH: car state and ring indices read + written once, phase/elapsed r/w, actions; per
+    # actor step of the launch: observation, reward, done, arrivals
+    bytes_env = 2 * (8 * cars_env + 8 * R) + 4 * I + 2 * 8 * I + spl * (4 * (2 * r + I) + 4 * I + 1 + 2 * arr_per_step)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -676,7 +712,7 @@ def b200_arm(a):
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "kernel": "te_step_kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_env_step": bytes_env, "cars_per_env": cars_env,
+                         "actor_steps_per_launch": spl, "algorithmic_bytes_per_env_launch": bytes_env, "cars_per_env": cars_env,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "note": "the fused K-tick kernel is issue/FP64-pipe bound, not HBM bound (SURVEY.md 8d); see roofline_issue"},
             "roofline_flush": {"bound": "hbm", "achieved": flush_gbs, "peak": peak, "unit": "GB/s", "frac": flush_gbs / peak,

@@ -138,6 +138,22 @@ int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16_t *roads, 
 int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
             int memspace, void *stream);
 
+/* te_step for a SUBSET of the envs: envs whose env_mask byte is zero are not stepped - their state, arrival stream and
+   rows of obs / reward / done stay untouched.  For learners that step their env slots at different times (A3C worker
+   threads, a3c.py:66-72: traffic_env_b200.pool.EnvPool steps whichever slots have an action ready). */
+int te_step_masked(te_handle *h, const uint8_t *actions, const uint8_t *env_mask, int32_t k_ticks, float *obs, float *reward,
+                   uint8_t *done, int memspace, void *stream);
+
+/* n_steps actor steps in ONE launch under one controller decision: the env state stays in shared memory for
+   n_steps * k_ticks ticks (<= 64); obs float[n_steps, E, 2r+I], reward float[n_steps, E, I], done uint8[n_steps, E] hold
+   every actor step's results exactly as n_steps calls of te_step with the same action would produce them.
+   controller TE_CTRL_GIVEN: `actions` uint8[E, I] is the input.  TE_CTRL_GREEDY: the kernel evaluates the reference's
+   greedy controller (algorithms/greedy.py:14-16, its decision holds for `--spacing` = n_steps actor steps) on the ring
+   counts at launch and writes the chosen actions to `actions` (nullable).  Not for TE_AUTO_RESET handles. */
+enum te_controller { TE_CTRL_GIVEN = 0, TE_CTRL_GREEDY = 1 };
+int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks, float *obs,
+                  float *reward, uint8_t *done, int memspace, void *stream);
+
 /* The same actor step with its results as compact WIRE RECORDS, one per env (what te_step(TE_HOST) moves over PCIe
    internally): u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done, `stride` bytes apart
    (te_wire_layout) - 2.5 x fewer bytes than the float observation; the integer-valued observation entries

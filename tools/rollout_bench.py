@@ -2,8 +2,9 @@
 (algorithms/a3c.py:52-63 `epoch`: obs -> policy -> env.step -> (obs, reward, done)) against the batched GPU env,
 with a stand-in policy of the learners' I/O shape (obs f32[81] -> bool[9]; TensorFlow 1 cannot run here).
 
-  mode "threads": T Python threads (FLAGS.threads), each on its own single-env proxy (traffic_env_b200.pool),
-                  the device stepping all slots in one launch per round; host obs / action traffic every step.
+  mode "threads": T Python threads (FLAGS.threads), each on its own single-env proxy (traffic_env_b200.pool); the
+                  device steps whichever slots have an action queued with one masked launch (no lock-step round: a
+                  slow thread only delays itself); host obs / action traffic every step.
   mode "device" : one loop over E env slots, policy = one torch matmul on the device, obs / reward / done stay in
                   HBM (VecTrafficEnv.step_device), auto-reset on done or after 120 actor steps (episode_len).
 
@@ -44,7 +45,8 @@ def run_threads(T, steps):
     dt = time.perf_counter() - t0
     st = pool.vec.stats()
     return {"mode": "threads", "threads": T, "steps_per_thread": steps, "actor_steps_per_sec": st["actor_steps"] / dt,
-            "vehicle_updates_per_sec": st["vehicle_updates"] / dt, "launches": pool.launches, "wall_s": dt}
+            "vehicle_updates_per_sec": st["vehicle_updates"] / dt, "launches": pool.launches,
+            "mean_slots_per_launch": pool.stepped / max(pool.launches, 1), "wall_s": dt}
 
 
 def run_device(E, steps):

@@ -8,15 +8,19 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libtraffic_b200.so")
+if os.environ.get("TRAFFIC_B200_SO"):
+    # developer switch for A/B measurements of kernel variants (tools/ab_variants.py): another build of the SAME library
+    SO_PATH = os.path.abspath(os.environ["TRAFFIC_B200_SO"])
 
 TE_HOST, TE_DEVICE = 0, 1
 TE_LEARN_SWITCH, TE_REMI, TE_AUTO_RESET, TE_VALIDATE, TE_ORDERED_TRANSFERS = 1, 2, 4, 8, 16
 TE_ARRIVALS_NONE, TE_ARRIVALS_INJECTED, TE_ARRIVALS_PHILOX = 0, 1, 2
 TE_PARAMS, TE_CAP = 10, 20
+TE_CTRL_GIVEN, TE_CTRL_GREEDY = 0, 1
 
 EXPORTS = [
     "te_default_config", "te_device_count", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
-    "te_reset", "te_set_arrivals", "te_step", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
+    "te_reset", "te_set_arrivals", "te_step", "te_step_masked", "te_step_multi", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
     "te_greedy_actions", "te_get_state", "te_set_state", "te_get_stats", "te_get_trip_times",
     "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_fdiv_const_exhaustive", "te_test_philox",
 ]
@@ -81,6 +85,8 @@ def load():
     L.te_step.argtypes = [vp, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_raw.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.te_step_wire.argtypes = [vp, vp, i32, vp, C.c_int, vp]
+    L.te_step_masked.argtypes = [vp, vp, vp, i32, vp, vp, vp, C.c_int, vp]
+    L.te_step_multi.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_wire_layout.argtypes = [vp, C.POINTER(TeWireLayout)]
     L.te_expand_wire.argtypes = [vp, vp, i32, vp, vp, vp]
     L.te_remi_reward.argtypes = [vp, vp, C.c_int, vp]

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libtraffic_b200.so")
-SOURCES = ["te_api.cu"]
+SOURCES = ["te_api.cu", "te_host.cpp"]
 HEADERS = ["te_kernels.cuh", "te_math.cuh", os.path.join("..", "..", "include", "traffic_b200.h")]
 
 
@@ -26,21 +26,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: developer builds of kernel variants for A/B measurements (tools/ab_variants.py)."""
+    if out is None and not force and not needs_build():
         return SO
     cmd = [nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "--fmad=false",  # the IDM arithmetic is spelled with explicit _rn intrinsics; never contract anything else
-           "-Xptxas", "-v" if verbose else "-O3",
-           "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+           "-Xptxas", "-v" if verbose else "-O3"] + ["-D" + d for d in defines] + [
+           "-o", out or SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return SO
+    return out or SO
 
 
 if __name__ == "__main__":

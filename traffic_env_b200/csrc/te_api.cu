@@ -42,26 +42,21 @@ static int fail(const char *fmt, ...) {
   } while (0)
 
 // ---- host side of the wire format (te_kernels.cuh: wire_stride_bytes): expand compact env records into the caller's
-// float observation / reward / done arrays.  Plain loops (the compiler vectorises the byte -> float conversion); the
-// work is memory-bound and overlapped with the simulation of the following slices (ExpandPool).
+// float observation / reward / done arrays (te_host.cpp).  The work is memory-bound and overlapped with the simulation
+// of the following slices (ExpandPool).
+void te_expand_records_host(const unsigned char *recs, int r, int I, int stride, long long n, float *obs, float *reward,
+                            uint8_t *done);   // te_host.cpp
 static void expand_records(const unsigned char *recs, int r, int I, int stride, long long n, float *obs, float *reward,
                            uint8_t *done) {
-  const int ol = 2 * r + I;
-  for (long long e = 0; e < n; e++) {
-    const unsigned char *rec = recs + (size_t)e * stride;
-    float *o = obs + (size_t)e * ol;
-    for (int k = 0; k < 2 * r; k++) o[k] = (float)rec[k];
-    memcpy(o + 2 * r, rec + 2 * r, (size_t)I * 4);
-    memcpy(reward + (size_t)e * I, rec + 2 * r + 4 * I, (size_t)I * 4);
-    done[e] = rec[2 * r + 8 * I];
-  }
+  te_expand_records_host(recs, r, I, stride, n, obs, reward, done);
 }
 
 // A few helper threads per handle that wait for a slice's device-to-host copy (CUDA event) and expand it while the
 // GPU simulates the next slices.  Slices are dealt round-robin; the calling thread takes its share too.
 struct ExpandJob {
   const unsigned char *recs; float *obs, *reward; uint8_t *done;
-  int r, I, stride, nslice, per, E;
+  const uint8_t *mask;           // nullable (host pointer): only envs with a non-zero byte were stepped
+  int r, I, stride, nslice, per, E, nsteps;
   cudaEvent_t *copied;
 };
 struct ExpandPool {
@@ -79,8 +74,17 @@ struct ExpandPool {
       if (cudaEventSynchronize(j.copied[k]) != cudaSuccess) { failed.store(1); continue; }
       const int e0 = k * j.per, ne = std::min(j.per, j.E - e0);
       if (ne <= 0) continue;
-      expand_records(j.recs + (size_t)e0 * j.stride, j.r, j.I, j.stride, ne, j.obs + (size_t)e0 * (2 * j.r + j.I),
-                     j.reward + (size_t)e0 * j.I, j.done + e0);
+      const int ol = 2 * j.r + j.I;
+      for (int st = 0; st < j.nsteps; st++) {
+        const size_t eo = (size_t)st * j.E + e0;       // [nsteps][E] env slots
+        if (!j.mask) {
+          expand_records(j.recs + eo * j.stride, j.r, j.I, j.stride, ne, j.obs + eo * ol, j.reward + eo * j.I, j.done + eo);
+        } else {
+          for (int e = 0; e < ne; e++)
+            if (j.mask[e0 + e])
+              expand_records(j.recs + (eo + e) * j.stride, j.r, j.I, j.stride, 1, j.obs + (eo + e) * ol, j.reward + (eo + e) * j.I, j.done + eo + e);
+        }
+      }
     }
   }
   void start(int dev, int n) {
@@ -139,16 +143,18 @@ struct te_handle {
   long long *d_sched_off;
   short *d_sched_roads;
   uint32_t *d_gap_cdf;
+  IdmConst *d_idm;
   // staging for TE_HOST calls
   uint8_t *d_actions, *d_done, *d_mask, *d_init_phase;
   float *d_obs_f, *d_reward;
   int *d_obs_i, *d_cars;
   float *w; TripRecord *d_trips; unsigned long long *d_trip_count; long long trip_cap;
   int warps;
+  int G, threads;        // env instances per CTA, threads per CTA (G * R rounded up to whole warps)
   int smem_optin;
   // wire path of the host API
   unsigned char *d_wire, *h_wire;   // [E][wire_stride] device / page-locked host
-  int wire_stride, host_slices;
+  int wire_stride, host_slices, wire_steps;
   cudaEvent_t ev_copy[64];
   ExpandPool *pool;
 };
@@ -159,20 +165,41 @@ struct te_handle {
 // x 2 CTAs, 101.7 KB each; 3x3 grid: 64 threads x 16 CTAs).
 typedef void (*step_kernel_t)(const StepParams);
 struct StepVariant { step_kernel_t fn; int maxt; };
-static StepVariant step_variant_for(int threads, bool validate) {
-  if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
-    if (threads <= 256) return {te_step_kernel<256, 2, true>, 256};
-    if (threads <= 512) return {te_step_kernel<512, 1, true>, 512};
-    return {te_step_kernel<768, 1, true>, 768};
-  }
-  if (threads <= 64) return {te_step_kernel<64, 16, false>, 64};   // default 3x3 grid: 2 warps per env, 16 envs per SM
-  if (threads <= 128) return {te_step_kernel<128, 8, false>, 128};
-  if (threads <= 256) return {te_step_kernel<256, 4, false>, 256};
-  if (threads <= 448) return {te_step_kernel<448, 2, false>, 448};
-  if (threads <= 512) return {te_step_kernel<512, 2, false>, 512};
-  if (threads <= 768) return {te_step_kernel<768, 1, false>, 768};
-  return {te_step_kernel<1024, 1, false>, 1024};
+#ifndef TE_FAST_ARCH
+#define TE_FAST_ARCH 1   // compile the car loop a second time for the reference's archetype (IdmConst.pow2 && delta_is_four)
+#endif
+template <int MAXT, int MINB, bool VALIDATE, bool GROUPED>
+static StepVariant pick_fa(bool fa) {
+#if TE_FAST_ARCH
+  if (fa) return {te_step_kernel<MAXT, MINB, VALIDATE, true, GROUPED>, MAXT};
+#endif
+  (void)fa;
+  return {te_step_kernel<MAXT, MINB, VALIDATE, false, GROUPED>, MAXT};
 }
+// threads = rows of the CTA; grouped = several env instances per CTA (small grids, te_create)
+static StepVariant step_variant_for(int threads, bool validate, bool fa, bool grouped) {
+  if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
+    if (threads <= 256) return pick_fa<256, 2, true, false>(false);
+    if (threads <= 512) return pick_fa<512, 1, true, false>(false);
+    return pick_fa<768, 1, true, false>(false);
+  }
+  if (grouped) {
+    if (threads <= 64) return pick_fa<64, 16, false, true>(fa);
+    if (threads <= 96) return pick_fa<96, 10, false, true>(fa);   // default 3x3 grid: two envs (2 x 48 roads) on three warps, 20 envs per SM
+    if (threads <= 128) return pick_fa<128, 8, false, true>(fa);
+    if (threads <= 160) return pick_fa<160, 6, false, true>(fa);
+    if (threads <= 192) return pick_fa<192, 5, false, true>(fa);
+    return pick_fa<256, 4, false, true>(fa);
+  }
+  if (threads <= 64) return pick_fa<64, 16, false, false>(fa);
+  if (threads <= 128) return pick_fa<128, 8, false, false>(fa);
+  if (threads <= 256) return pick_fa<256, 4, false, false>(fa);
+  if (threads <= 448) return pick_fa<448, 2, false, false>(fa);
+  if (threads <= 512) return pick_fa<512, 2, false, false>(fa);
+  if (threads <= 768) return pick_fa<768, 1, false, false>(fa);
+  return pick_fa<1024, 1, false, false>(fa);
+}
+static bool fast_arch(const te_handle *h);
 
 // The double literals of the IDM update live in constant memory (te_math.cuh: g_mc); one upload per device.
 static cudaError_t upload_math_consts() {
@@ -196,6 +223,8 @@ static void fill_idm(IdmConst &c, const float *a, float rate) {
   c.T_d = (double)a[7];
   c.pow2 = is_pow2_f(a[7]) && is_pow2_f(rate) && !getenv("TE_NO_POW2_SHORTCUT");
 }
+
+static bool fast_arch(const te_handle *h) { return h->base.idm.pow2 && h->base.idm.delta_is_four; }
 
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
 
@@ -257,7 +286,7 @@ static void free_handle(te_handle *h) {
   if (h->h_wire) cudaFreeHost(h->h_wire);
   for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   void *ptrs[] = {h->w, h->x, h->v, h->elapsed, h->phase, h->passed_dst, h->env, h->stats, h->d_nexts, h->d_up,
-                  h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_actions,
+                  h->d_entry_idx, h->d_sched_off, h->d_sched_roads, h->d_gap_cdf, h->d_idm, h->d_actions,
                   h->d_done, h->d_mask, h->d_init_phase, h->d_reward, h->d_obs_i /* d_obs_f aliases it */, h->d_cars,
                   h->d_trips, h->d_trip_count};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -309,12 +338,12 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->cfg = *cfg; h->device = cfg->device;
   h->x = h->v = h->w = nullptr; h->elapsed = nullptr; h->phase = h->passed_dst = nullptr; h->env = nullptr; h->stats = nullptr;
   h->d_nexts = h->d_up = nullptr; h->d_entry_idx = nullptr; h->d_sched_off = nullptr;
-  h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
+  h->d_sched_roads = nullptr; h->d_gap_cdf = nullptr; h->d_idm = nullptr; h->d_actions = h->d_done = h->d_mask = h->d_init_phase = nullptr;
   h->d_obs_f = h->d_reward = nullptr; h->d_obs_i = h->d_cars = nullptr; h->d_trips = nullptr; h->d_trip_count = nullptr;
   h->stream = h->stream2 = h->stream_copy = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = h->ev_copied = nullptr;
   for (cudaEvent_t &e : h->ev_slice) e = nullptr;
   for (cudaEvent_t &e : h->ev_copy) e = nullptr;
-  h->d_wire = h->h_wire = nullptr; h->pool = nullptr; h->wire_stride = 0; h->host_slices = 1;
+  h->d_wire = h->h_wire = nullptr; h->pool = nullptr; h->wire_stride = 0; h->host_slices = 1; h->wire_steps = 0;
   h->timed = false; h->trip_cap = 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUH(cudaSetDevice(h->device));
@@ -387,6 +416,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->wire_stride = wire_stride_bytes(h->r, h->I);
   CUH(dalloc(&h->d_wire, E * (size_t)h->wire_stride));
   CUH(cudaHostAlloc((void **)&h->h_wire, E * (size_t)h->wire_stride, cudaHostAllocDefault));
+  h->wire_steps = 1;
   {
     // Host path: the batch is launched in slices (te_step, TE_HOST) and a few helper threads expand the compact
     // records of finished slices into the caller's float arrays meanwhile.  TE_HOST_SLICES / TE_HOST_THREADS tune it.
@@ -444,21 +474,42 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
   p.gamma = cfg->gamma;
   fill_idm(p.idm, cfg->archetype, cfg->rate);
+  CUH(dalloc(&h->d_idm, 1));
+  CUH(cudaMemcpy(h->d_idm, &p.idm, sizeof(IdmConst), cudaMemcpyHostToDevice));
+  p.idm_g = h->d_idm;
   p.x = h->x; p.v = h->v; p.w = h->w; p.trips = h->d_trips; p.trip_count = h->d_trip_count; p.trip_cap = h->trip_cap;
   p.elapsed = h->elapsed; p.phase = h->phase; p.passed_dst = h->passed_dst;
   p.env = h->env; p.stats = h->stats; p.nexts = h->d_nexts; p.up = h->d_up; p.entry_idx = h->d_entry_idx;
   p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
   p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0; p.sched_first = 0;
+  p.nsteps = 1; p.controller = CTRL_GIVEN; p.actions_out = nullptr; p.env_mask = nullptr;
 
-  // one thread per (padded) road: warp w owns roads [32w, 32w + 32)
-  h->warps = h->Rp / GROUP_ROADS;
+  // One thread per road.  Small grids put G env instances on one CTA (its rows are the G * R roads of those envs) so
+  // that no lane is a padding lane and a warp's car list is long: G in 1..4 with at most 256 rows, chosen for the
+  // fewest padding lanes (ties: the smaller G).  Default 3x3 grid: R = 48 -> G = 2, 96 threads, three warps.
+  // Large grids: G = 1, the CTA padded like the HBM rows (Rp).
   if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
-  CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const bool validate = (cfg->flags & TE_VALIDATE) != 0;
-  const StepVariant sv = step_variant_for(h->Rp, validate);
-  if (h->Rp > sv.maxt) { free_handle(h); return fail("te_create: %d roads exceed the largest%s kernel variant (%d)", h->Rp, validate ? " validate-mode" : "", sv.maxt); }
-  const int smem_max = smem_bytes(sv.maxt, validate, MAX_K, h->n_entry);
+  h->G = 1; h->threads = h->Rp;
+  if (!validate && h->R < 128) {
+    double best = (double)(h->Rp - h->R) / h->Rp;
+    for (int g = 2; g <= 4 && g * h->R <= 256; g++) {
+      const int th = (g * h->R + 31) / 32 * 32;
+      const double waste = (double)(th - g * h->R) / th;
+      if (waste < best - 1e-9) { best = waste; h->G = g; h->threads = th; }
+    }
+  }
+  if (const char *ev = getenv("TE_ENVS_PER_CTA")) {   // study knob
+    const int g = atoi(ev);
+    if (g >= 1 && g <= 8 && g * h->R <= 1024 && !validate) { h->G = g; h->threads = g == 1 ? h->Rp : (g * h->R + 31) / 32 * 32; }
+  }
+  h->warps = h->threads / GROUP_ROADS;
+  p.G = h->G;
+  CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const StepVariant sv = step_variant_for(h->threads, validate, fast_arch(h), h->G > 1);
+  if (h->threads > sv.maxt) { free_handle(h); return fail("te_create: %d roads exceed the largest%s kernel variant (%d)", h->threads, validate ? " validate-mode" : "", sv.maxt); }
+  const int smem_max = smem_bytes(sv.maxt, validate, MAX_K, h->n_entry, h->G);
   if (smem_max > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", smem_max, h->smem_optin); }
   CUH(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 
@@ -564,37 +615,76 @@ extern "C" int te_set_arrivals(te_handle *h, const int64_t *offsets, const int16
   return 0;
 }
 
-// wire_only: the caller wants the compact records themselves (te_step_wire): `obs` is the record buffer
-// (device memory for TE_DEVICE; for TE_HOST the records land in the handle's page-locked buffer and `obs` receives them).
-static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, void *obs, float *reward, uint8_t *done,
-                       int memspace, void *stream, bool wire_only = false) {
-  if (!h || !actions || !obs || (!wire_only && (!reward || !done))) return fail("te_step: null argument");
-  if (wire_only && K > WIRE_MAX_K) return fail("te_step_wire: k_ticks must be <= %d (passed counts travel as bytes)", WIRE_MAX_K);
-  if (K < 1 || K > MAX_K) return fail("te_step: k_ticks must be in [1, %d]", MAX_K);
-  if (h->cfg.arrival_mode == TE_ARRIVALS_INJECTED && !h->base.sched_off) return fail("te_step: no arrival schedule set");
+// One request to the step kernel.  wire_only: the caller wants the compact records themselves (te_step_wire): `obs` is the
+// record buffer.  nsteps > 1 / controller / env_mask: te_step_multi / te_step_masked.
+struct StepReq {
+  const uint8_t *actions = nullptr;   // CTRL_GIVEN: input [E][I]; CTRL_GREEDY: output (nullable)
+  int K = 1, raw = 0, nsteps = 1, controller = CTRL_GIVEN;
+  void *obs = nullptr; float *reward = nullptr; uint8_t *done = nullptr;
+  const uint8_t *env_mask = nullptr;
+  int memspace = TE_HOST; void *stream = nullptr;
+  bool wire_only = false;
+  const char *who = "te_step";
+};
+
+static int ensure_wire_steps(te_handle *h, int nsteps) {
+  if (nsteps <= h->wire_steps) return 0;
+  CU(cudaDeviceSynchronize());
+  const size_t bytes = (size_t)nsteps * h->cfg.num_envs * h->wire_stride;
+  if (h->d_wire) { cudaFree(h->d_wire); h->d_wire = nullptr; }
+  if (h->h_wire) { cudaFreeHost(h->h_wire); h->h_wire = nullptr; }
+  h->wire_steps = 0;
+  CU(dalloc(&h->d_wire, bytes));
+  CU(cudaHostAlloc((void **)&h->h_wire, bytes, cudaHostAllocDefault));
+  h->wire_steps = nsteps;
+  return 0;
+}
+
+static int launch_step(te_handle *h, const StepReq &q) {
+  const int K = q.K, raw = q.raw, nsteps = q.nsteps;
+  const bool greedy = q.controller == CTRL_GREEDY;
+  if (!h || !q.obs || (!greedy && !q.actions) || (!q.wire_only && (!q.reward || !q.done))) return fail("%s: null argument", q.who);
+  if (K < 1 || K > MAX_K) return fail("%s: k_ticks must be in [1, %d]", q.who, MAX_K);
+  if (nsteps < 1 || nsteps * K > MAX_K) return fail("%s: n_steps * k_ticks must be in [1, %d]", q.who, MAX_K);
+  if (q.wire_only && K > WIRE_MAX_K) return fail("te_step_wire: k_ticks must be <= %d (passed counts travel as bytes)", WIRE_MAX_K);
+  if (nsteps > 1 && (h->cfg.flags & TE_AUTO_RESET)) return fail("%s: a TE_AUTO_RESET handle resets between te_step calls; multi-step launches need a handle without it", q.who);
+  if (h->cfg.arrival_mode == TE_ARRIVALS_INJECTED && !h->base.sched_off) return fail("%s: no arrival schedule set", q.who);
   CU(cudaSetDevice(h->device));
-  cudaStream_t st = pick_stream(h, stream);
+  cudaStream_t st = pick_stream(h, q.stream);
   const size_t E = (size_t)h->cfg.num_envs;
   const size_t obs_len = raw ? (size_t)(2 * h->r + 2 * h->I) : (size_t)(2 * h->r + h->I);
+  const bool host = q.memspace == TE_HOST;
+  const bool use_wire = !raw && K <= WIRE_MAX_K && (host || q.wire_only);
+  if (host && nsteps > 1 && !use_wire) return fail("%s: multi-step launches with host buffers need k_ticks <= %d", q.who, WIRE_MAX_K);
   StepParams p = h->base;
-  p.K = K; p.raw = raw;
-  if (memspace == TE_HOST) {
-    CU(cudaMemcpyAsync(h->d_actions, actions, E * h->I, cudaMemcpyHostToDevice, st));
-    p.actions = h->d_actions; p.obs_f = h->d_obs_f; p.obs_i = h->d_obs_i; p.reward = h->d_reward; p.done = h->d_done;
+  p.K = K; p.raw = raw; p.nsteps = nsteps; p.controller = q.controller; p.actions_out = nullptr; p.env_mask = q.env_mask;
+  if (host) {
+    if (!greedy) CU(cudaMemcpyAsync(h->d_actions, q.actions, E * h->I, cudaMemcpyHostToDevice, st));
+    if (q.env_mask) { CU(cudaMemcpyAsync(h->d_mask, q.env_mask, E, cudaMemcpyHostToDevice, st)); p.env_mask = h->d_mask; }
+    p.actions = h->d_actions; p.actions_out = greedy ? h->d_actions : nullptr;
+    p.obs_f = h->d_obs_f; p.obs_i = h->d_obs_i; p.reward = h->d_reward; p.done = h->d_done;
+    if (use_wire) {
+      if (int rc = ensure_wire_steps(h, nsteps)) return rc;
+      p.wire = h->d_wire; p.wire_stride = h->wire_stride;
+    }
   } else {
-    p.actions = actions; p.obs_f = (float *)obs; p.obs_i = (int *)obs; p.reward = reward; p.done = done;
-    if (wire_only) { p.wire = (unsigned char *)obs; p.wire_stride = h->wire_stride; }
+    p.actions = q.actions; p.actions_out = greedy ? const_cast<uint8_t *>(q.actions) : nullptr;
+    p.obs_f = (float *)q.obs; p.obs_i = (int *)q.obs; p.reward = q.reward; p.done = q.done;
+    if (q.wire_only) { p.wire = (unsigned char *)q.obs; p.wire_stride = h->wire_stride; }
   }
   if (!raw && (h->cfg.flags & TE_AUTO_RESET)) {
-    te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, nullptr, nullptr, 1);
+    te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, p.env_mask, nullptr, 1);
     CU(cudaGetLastError());
   }
   const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
-  const StepVariant sv = step_variant_for(h->Rp, validate);
-  const int smem = smem_bytes(sv.maxt, validate, K, h->n_entry);
+  const StepVariant sv = step_variant_for(h->threads, validate, fast_arch(h), h->G > 1);
+  const int smem = smem_bytes(sv.maxt, validate, K * nsteps, h->n_entry, h->G);
+  const int G = h->G;
+  p.G = G;
   CU(cudaEventRecord(h->ev0, st));
-  if (memspace != TE_HOST) {
-    sv.fn<<<h->cfg.num_envs, h->Rp, smem, st>>>(p);
+  if (!host) {
+    p.env0 = 0; p.env_end = h->cfg.num_envs;
+    sv.fn<<<(h->cfg.num_envs + G - 1) / G, h->threads, smem, st>>>(p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
@@ -603,51 +693,53 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
   // Host buffers: the batch is launched in slices on two alternating streams (the tail of one slice overlaps the
   // head of the next), and a third stream copies each finished slice's results to the host while the following slices
   // are simulated (envs are independent: any slicing gives the same results).  Fused steps of up to WIRE_MAX_K ticks
-  // travel as compact wire records (one copy per slice, 2.5 x fewer bytes than the float observation) that the
-  // handle's helper threads expand into the caller's arrays while the GPU works on the next slices.
+  // travel as compact wire records (one copy per slice and actor step, 2.5 x fewer bytes than the float observation)
+  // that the handle's helper threads expand into the caller's arrays while the GPU works on the next slices.
   const int E_i = h->cfg.num_envs;
   const int nslice = h->host_slices;
-  const int per = (E_i + nslice - 1) / nslice;
-  const bool use_wire = !raw && K <= WIRE_MAX_K;
-  if (use_wire) { p.wire = h->d_wire; p.wire_stride = h->wire_stride; }
+  const int per = ((E_i + nslice - 1) / nslice + G - 1) / G * G;   // whole CTAs (G envs each) per slice
   CU(cudaEventRecord(h->ev_fork, st));               // actions (and the auto-reset) are complete on `st`
   CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   cudaStream_t lanes[2] = {st, h->stream2};
   const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;
+  unsigned char *host_wire = q.wire_only ? (unsigned char *)q.obs : h->h_wire;
+  const size_t wstep = E * (size_t)h->wire_stride;   // records of one actor step
   int nk = 0;
   for (int k = 0, e0 = 0; e0 < E_i; k++, e0 += per) {
     const int ne = (E_i - e0) < per ? (E_i - e0) : per;
     cudaStream_t cs = lanes[k & 1];
-    p.env0 = e0;
-    sv.fn<<<ne, h->Rp, smem, cs>>>(p);
+    p.env0 = e0; p.env_end = e0 + ne;
+    sv.fn<<<(ne + G - 1) / G, h->threads, smem, cs>>>(p);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_slice[k], cs));
     CU(cudaStreamWaitEvent(h->stream_copy, h->ev_slice[k], 0));
     if (use_wire) {
-      unsigned char *host_dst = wire_only ? (unsigned char *)obs : h->h_wire;
-      CU(cudaMemcpyAsync(host_dst + (size_t)e0 * h->wire_stride, h->d_wire + (size_t)e0 * h->wire_stride,
-                         (size_t)ne * h->wire_stride, cudaMemcpyDeviceToHost, h->stream_copy));
+      for (int j = 0; j < nsteps; j++)
+        CU(cudaMemcpyAsync(host_wire + j * wstep + (size_t)e0 * h->wire_stride, h->d_wire + j * wstep + (size_t)e0 * h->wire_stride,
+                           (size_t)ne * h->wire_stride, cudaMemcpyDeviceToHost, h->stream_copy));
       CU(cudaEventRecord(h->ev_copy[k], h->stream_copy));
     } else {
-      CU(cudaMemcpyAsync((char *)obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
+      CU(cudaMemcpyAsync((char *)q.obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
                          cudaMemcpyDeviceToHost, h->stream_copy));
-      CU(cudaMemcpyAsync(reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
+      CU(cudaMemcpyAsync(q.reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
                          cudaMemcpyDeviceToHost, h->stream_copy));
-      CU(cudaMemcpyAsync(done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
+      CU(cudaMemcpyAsync(q.done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
     }
     nk = k + 1;
   }
+  if (greedy && q.actions)   // the controller's choice, for the caller
+    CU(cudaMemcpyAsync(const_cast<uint8_t *>(q.actions), h->d_actions, E * h->I, cudaMemcpyDeviceToHost, h->stream_copy));
   CU(cudaEventRecord(h->ev_join, h->stream2));
   CU(cudaEventRecord(h->ev_copied, h->stream_copy));
   CU(cudaStreamWaitEvent(st, h->ev_join, 0));
   CU(cudaStreamWaitEvent(st, h->ev_copied, 0));
   CU(cudaEventRecord(h->ev1, st));
   h->timed = true;
-  if (use_wire && !wire_only) {
-    ExpandJob j = {h->h_wire, (float *)obs, reward, done, h->r, h->I, h->wire_stride, nk, per, E_i, h->ev_copy};
+  if (use_wire && !q.wire_only) {
+    ExpandJob j = {h->h_wire, (float *)q.obs, q.reward, q.done, q.env_mask, h->r, h->I, h->wire_stride, nk, per, E_i, nsteps, h->ev_copy};
     const bool ok = h->pool->run(j);
     CU(cudaStreamSynchronize(st));
-    if (!ok) return fail("te_step: a device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!ok) return fail("%s: a device-to-host copy failed: %s", q.who, cudaGetErrorString(cudaGetLastError()));
     return 0;
   }
   CU(cudaStreamSynchronize(st));
@@ -656,11 +748,30 @@ static int launch_step(te_handle *h, const uint8_t *actions, int K, int raw, voi
 
 extern "C" int te_step(te_handle *h, const uint8_t *actions, int32_t k_ticks, float *obs, float *reward, uint8_t *done,
                        int memspace, void *stream) {
-  return launch_step(h, actions, k_ticks, 0, obs, reward, done, memspace, stream);
+  StepReq q; q.actions = actions; q.K = k_ticks; q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace; q.stream = stream;
+  return launch_step(h, q);
+}
+
+extern "C" int te_step_masked(te_handle *h, const uint8_t *actions, const uint8_t *env_mask, int32_t k_ticks, float *obs,
+                              float *reward, uint8_t *done, int memspace, void *stream) {
+  if (!env_mask) return fail("te_step_masked: null mask");
+  StepReq q; q.actions = actions; q.K = k_ticks; q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace; q.stream = stream;
+  q.env_mask = env_mask; q.who = "te_step_masked";
+  return launch_step(h, q);
+}
+
+extern "C" int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks, float *obs,
+                             float *reward, uint8_t *done, int memspace, void *stream) {
+  if (controller != TE_CTRL_GIVEN && controller != TE_CTRL_GREEDY) return fail("te_step_multi: unknown controller %d", controller);
+  StepReq q; q.actions = actions; q.K = k_ticks; q.nsteps = n_steps; q.controller = controller == TE_CTRL_GREEDY ? CTRL_GREEDY : CTRL_GIVEN;
+  q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace; q.stream = stream; q.who = "te_step_multi";
+  return launch_step(h, q);
 }
 
 extern "C" int te_step_wire(te_handle *h, const uint8_t *actions, int32_t k_ticks, void *records, int memspace, void *stream) {
-  return launch_step(h, actions, k_ticks, 0, records, nullptr, nullptr, memspace, stream, true);
+  StepReq q; q.actions = actions; q.K = k_ticks; q.obs = records; q.memspace = memspace; q.stream = stream; q.wire_only = true;
+  q.who = "te_step_wire";
+  return launch_step(h, q);
 }
 
 extern "C" int te_wire_layout(const te_handle *h, te_wire_layout_t *out) {
@@ -678,7 +789,9 @@ extern "C" int te_expand_wire(const te_handle *h, const void *records, int32_t c
 
 extern "C" int te_step_raw(te_handle *h, const uint8_t *actions, int32_t *obs, float *reward, uint8_t *done,
                            int memspace, void *stream) {
-  return launch_step(h, actions, 1, 1, obs, reward, done, memspace, stream);
+  StepReq q; q.actions = actions; q.K = 1; q.raw = 1; q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace;
+  q.stream = stream; q.who = "te_step_raw";
+  return launch_step(h, q);
 }
 
 extern "C" int te_remi_reward(te_handle *h, float *reward, int memspace, void *stream) {
@@ -875,7 +988,7 @@ extern "C" int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_
   CU(cudaDeviceSynchronize());
   const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;
   // same dynamic shared-memory footprint as the step kernel, so the same number of CTAs (copies in flight) per SM
-  const int stage_smem = smem_bytes(step_variant_for(h->Rp, validate).maxt, validate, 10, h->n_entry);
+  const int stage_smem = smem_bytes(step_variant_for(h->Rp, validate, false, false).maxt, validate, 10, h->n_entry, 1);
   CU(cudaFuncSetAttribute(te_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_smem));
   StepParams p = h->base;
   p.K = 10;
@@ -932,13 +1045,17 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   fill_idm(c, a, rate);
   float *d[7];
   const float *src[5] = {xl, vl, ll, x, v};
+  IdmConst *dc = nullptr;
+  CU(cudaMalloc(&dc, sizeof(IdmConst)));
+  CU(cudaMemcpy(dc, &c, sizeof(IdmConst), cudaMemcpyHostToDevice));
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
   for (int i = 0; i < 5; i++) CU(cudaMemcpy(d[i], src[i], n * 4, cudaMemcpyHostToDevice));
-  te_test_idm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(c, d[0], d[1], d[2], d[3], d[4], d[5], d[6], n);
+  te_test_idm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(c, dc, d[0], d[1], d[2], d[3], d[4], d[5], d[6], n);
   CU(cudaGetLastError());
   CU(cudaMemcpy(x_out, d[5], n * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(v_out, d[6], n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 7; i++) cudaFree(d[i]);
+  cudaFree(dc);
   return 0;
 }
 
@@ -955,18 +1072,21 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   if (const char *ev = getenv("TE_PEAK_WARPS_PER_SM")) { const int w = atoi(ev); if (w >= 1 && w <= 32) { threads = 32 * w; blocks = sms; } }
   float *sink = nullptr;
   CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
+  IdmConst *dc = nullptr;
+  CU(cudaMalloc(&dc, sizeof(IdmConst)));
+  CU(cudaMemcpy(dc, &c, sizeof(IdmConst), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, iters / 4 + 1, sink);  // warm-up
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters / 4 + 1, sink);  // warm-up
   CU(cudaEventRecord(e0));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, iters, sink);
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters, sink);
   CU(cudaEventRecord(e1));
   CU(cudaEventSynchronize(e1));
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
   *updates_per_sec = (double)threads * blocks * iters / (ms * 1e-3);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink); cudaFree(dc);
   return 0;
 }
 

@@ -43,6 +43,7 @@ constexpr int MAX_K = 64;
 
 enum : int { F_LEARN_SWITCH = 1, F_REMI = 2, F_AUTO_RESET = 4, F_VALIDATE = 8, F_ORDERED = 16 };
 enum : int { ARR_NONE = 0, ARR_INJECTED = 1, ARR_PHILOX = 2 };
+enum : int { CTRL_GIVEN = 0, CTRL_GREEDY = 1 };
 
 struct EnvScalars {
   float steps;            // np.float32 tick counter of the current episode (traffic_env.py:260,247)
@@ -73,12 +74,15 @@ struct StepParams {
   int V, r, R, Rp, I, n_entry;
   int num_envs;
   int env0;               // first env of this launch (te_step with host buffers launches the batch in slices)
+  int env_end;            // one past the last env of this launch
+  int G;                  // env instances per CTA (small grids share a CTA: te_api.cu envs_per_cta)
   float length;
   float det_thr_f;        // largest float <= (double)length - 10.0 (traffic_env.py:201: float32 - int64 types as float64):
                           // for every float x, (double)x > (double)length - 10.0  <=>  x > det_thr_f
   int flags, arrival_mode, K, raw, episode_len;
   float gamma;
   IdmConst idm;
+  const IdmConst *idm_g;   // the same constants in global memory (for the out-of-line generic IDM routine)
   // state (HBM)
   float *x, *v;           // [E][Rp][20]; slot 0 of a row carries packed ring indices (see pack_meta)
   float *w;               // [E][Rp][20] birth tick of each car (validate mode only, traffic_env.py:34,279)
@@ -102,6 +106,12 @@ struct StepParams {
   //   u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done | pad   (wire_stride bytes, see wire_layout)
   unsigned char *wire;
   int wire_stride;
+  // multi-step launches (te_step_multi): nsteps actor steps of K ticks each under one controller decision; the outputs
+  // of actor step j go to obs / reward / done / wire + j * (their size for num_envs envs)
+  int nsteps;
+  int controller;               // CTRL_GIVEN: `actions` is read; CTRL_GREEDY: computed in the kernel from the ring counts
+  uint8_t *actions_out;         // CTRL_GREEDY: the actions chosen, [E][I] (nullable)
+  const uint8_t *env_mask;      // nullable; [E], zero = this env is not stepped (te_step_masked)
   // arrivals
   const long long *sched_off;   // [E*(horizon+1)]
   const short *sched_roads;
@@ -124,11 +134,14 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
   return (uint32_t)leading | ((uint32_t)lastcar << 8) | ((uint32_t)detected << 16);
 }
 
-// Shared-memory layout of one CTA.  Every offset is a compile-time function of the kernel variant's row capacity
-// MAXT (>= Rp) so that the tick loop addresses shared memory with immediates; only the arrival-count table at the
-// very end has a run-time size (K * n_entry bytes).
+// Shared-memory layout of one CTA.  A CTA simulates G env instances (G = 1 for large grids; small grids share a CTA so
+// that no lane is a padding lane and a warp's car list is long): its rows are the G * R roads of those envs
+// ("super-roads": row g * R + road), per-intersection arrays are indexed g * I + intersection.  Every offset is a
+// compile-time function of the kernel variant's row capacity MAXT (>= G * R rounded up to whole warps) so that the tick
+// loop addresses shared memory with immediates; only the tail has a run-time size: per env the arrival-count table
+// (K * n_entry bytes), the Philox (draw, skip) snapshots before each tick and two per-env tick stamps.
 struct SmemLayout {
-  int xs, vs, ws, tabs, mbar, tailx, meta, wait, elapsed, ovf, snap, misc, warp, phase, act, pdst, cnt;
+  int xs, vs, ws, tabs, mbar, tailx, meta, wait, elapsed, ovf, rew, misc, warp, phase, act, pdst, cnt;
 };
 
 __host__ __device__ constexpr int align_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -147,8 +160,9 @@ __host__ __device__ constexpr SmemLayout make_layout(int maxt, bool validate) {
   L.wait = o; o += maxt * 4;
   L.elapsed = o; o += icap * 4;
   L.ovf = o; o += icap * 4;
-  L.snap = o; o += (MAX_K + 1) * 8;                     // Philox (draw, skip) before each tick
+  L.rew = o; o += icap * 4;
   L.misc = o; o += 32;
+  o = align_up(o, 16);
   L.warp = o; o += (maxt / GROUP_ROADS) * WARP_AREA;
   L.phase = o; o += icap;
   L.act = o; o += icap;
@@ -158,12 +172,23 @@ __host__ __device__ constexpr SmemLayout make_layout(int maxt, bool validate) {
 }
 
 static_assert(make_layout(64, false).warp % 16 == 0 && make_layout(448, false).warp % 16 == 0 && make_layout(256, true).warp % 16 == 0 &&
-              make_layout(1024, false).warp % 16 == 0 && WARP_AREA % 16 == 0 && make_layout(448, false).mbar % 8 == 0 &&
+              make_layout(1024, false).warp % 16 == 0 && make_layout(96, false).warp % 16 == 0 && make_layout(160, false).warp % 16 == 0 &&
+              make_layout(192, false).warp % 16 == 0 && WARP_AREA % 16 == 0 && make_layout(448, false).mbar % 8 == 0 &&
+              make_layout(96, false).mbar % 8 == 0 && make_layout(160, false).mbar % 8 == 0 &&
               make_layout(448, false).vs % 16 == 0 && make_layout(448, true).ws % 16 == 0 && make_layout(64, false).cnt % 16 == 0,
               "shared-memory layout alignment");
-__host__ __device__ constexpr int smem_bytes(int maxt, bool validate, int K, int n_entry) {
-  return make_layout(maxt, validate).cnt + align_up(K * (n_entry > 0 ? n_entry : 1), 16);
+// run-time tail, KT = ticks of the whole launch (nsteps * K):
+//   [G][cnt_stride] arrival counts | [G][KT + 1][2] Philox snapshots | [G][4] per-env words (ENVM_*)
+__host__ __device__ constexpr int cnt_stride_bytes(int KT, int n_entry) { return align_up(KT * (n_entry > 0 ? n_entry : 1), 4); }
+__host__ __device__ constexpr int tail_snap_offset(int KT, int n_entry, int G) { return align_up(G * cnt_stride_bytes(KT, n_entry), 8); }
+__host__ __device__ constexpr int smem_bytes(int maxt, bool validate, int KT, int n_entry, int G) {
+  return make_layout(maxt, validate).cnt + align_up(tail_snap_offset(KT, n_entry, G) + G * (KT + 1) * 8 + G * 16, 16);
 }
+enum : int { ENVM_OVF = 0,    // first overflowing tick of the current actor step (NO_OVERFLOW: none yet)
+             ENVM_ORD = 1,    // last tick of the launch (CTA-wide count) that needs ordered transfers
+             ENVM_TB = 2,     // ticks this env ran in the earlier actor steps of this launch
+             ENVM_SKIP = 3,   // env not stepped (env_mask)
+             ENVM_WORDS = 4 };
 
 // ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier: the env's ring planes are contiguous in HBM, so
 // one elected thread moves each plane with a single instruction while the other threads set up the tick loop.
@@ -246,9 +271,9 @@ struct Smem {
   float *xs, *vs, *ws, *tailx;
   uint32_t *meta;        // published after phase A: leading | lastcar << 8 | pre-pop leading << 16 | npop << 24
   int *wait, *elapsed, *ovf;
+  float *rew;            // reward of the finished actor step per intersection (for the return statistic)
   unsigned long long *mbar;
-  uint32_t *snap;
-  int *misc;             // [0] first overflowing tick, [1] tick needing ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer ticks, [6] cars that left the map
+  int *misc;             // CTA level: [0] envs still running, [1] last tick in which some env needed ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer env-ticks, [6] cars that left the map
   uint8_t *warp, *phase, *act, *pdst, *cnt;
   const PowfTables *tabs;  // glibc powf tables (global memory, L1-resident: read by ~0.4 % of the cars)
 };
@@ -258,13 +283,13 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) 
   s.xs = (float *)(base + L.xs); s.vs = (float *)(base + L.vs); s.ws = (float *)(base + L.ws);
   s.tailx = (float *)(base + L.tailx); s.mbar = (unsigned long long *)(base + L.mbar);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
-  s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.snap = (uint32_t *)(base + L.snap);
+  s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.rew = (float *)(base + L.rew);
   s.misc = (int *)(base + L.misc); s.warp = base + L.warp; s.phase = base + L.phase; s.act = base + L.act;
   s.pdst = base + L.pdst; s.cnt = base + L.cnt; s.tabs = &g_powf_tables;
   return s;
 }
 
-// Move the popped cars of road u to the tail of road d (advance_finished_cars -> add_car,
+// Move the popped cars of (super-)road u to the tail of (super-)road d (advance_finished_cars -> add_car,
 // traffic_env.py:126-132).  `chk` is the value of leading[d] the reference sees at that moment:
 // the pre-pop value when u < d (the reference inserts before d's own pops of this tick).
 // Returns the number of cars dropped on a full ring.
@@ -284,70 +309,88 @@ __device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int 
   return dropped;
 }
 
-template <int MAXT, int MINB, bool VALIDATE>
+constexpr int NO_OVERFLOW = 0x7fffffff;
+
+// GROUPED = false: one env per CTA (p.G == 1), everything about env groups folds away at compile time.
+template <int MAXT, int MINB, bool VALIDATE, bool FA, bool GROUPED>
 __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr SmemLayout L = make_layout(MAXT, VALIDATE);
   const Smem s = carve(smem_raw, L);
-  const int env = p.env0 + blockIdx.x;
+  const int G = GROUPED ? p.G : 1;
+  const int env_first = p.env0 + blockIdx.x * G;             // this CTA simulates envs [env_first, env_first + ng)
+  const int ng = GROUPED ? min(G, p.env_end - env_first) : 1;  // (the last CTA of a launch may hold fewer than G)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;                        // blockDim.x == G * R rounded up to whole warps
   const unsigned FULL = 0xffffffffu;
   const float INF = __int_as_float(0x7f800000);
   const bool learn_switch = (p.flags & F_LEARN_SWITCH) != 0;
-  EnvScalars *es = p.env + env;
+  const int KT = p.K * p.nsteps;                             // ticks of the whole launch
+  // te_step_masked: envs whose mask byte is zero are not stepped; a CTA with nothing to do retires at once
+  int nactive = ng;
+  if (p.env_mask) {
+    nactive = 0;
+    for (int g = 0; g < ng; g++) nactive += p.env_mask[env_first + g] != 0;
+    if (nactive == 0) return;
+  }
+  // run-time tail of the shared-memory layout (per env: arrival counts, Philox snapshots, ENVM words)
+  const int cnt_stride = cnt_stride_bytes(KT, p.n_entry);
+  uint32_t *const snap_base = reinterpret_cast<uint32_t *>(s.cnt + tail_snap_offset(KT, p.n_entry, G));
+  int *const envm = reinterpret_cast<int *>(snap_base + G * 2 * (KT + 1));
+  const int nrows = ng * p.R;                                // live rows (super-roads) of this CTA
+  const int nI = ng * p.I;
+  const size_t ibase = (size_t)env_first * p.I;              // the per-intersection arrays of consecutive envs are contiguous
 
-  // ------------------------------------------------------------ prologue: stage the env
-  // only the R real roads travel: the padding rows (threads R .. Rp-1) are set up in shared memory below
+  // ------------------------------------------------------------ prologue: stage the envs
+  // only the R real roads of an env travel (its padding rows in HBM do not); rows nrows .. blockDim.x-1 are set up below
   const uint32_t plane_bytes = (uint32_t)p.R * CAP * 4;   // multiple of 16: rows of 80 B
   if (tid == 0) {
     mbar_init(s.mbar, 1);
     fence_proxy_async();
-    mbar_expect_tx(s.mbar, plane_bytes * (VALIDATE ? 3u : 2u));
-    bulk_load(s.xs, p.x + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
-    bulk_load(s.vs, p.v + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
-    if (VALIDATE) bulk_load(s.ws, p.w + (size_t)env * p.Rp * CAP, plane_bytes, s.mbar);
+    mbar_expect_tx(s.mbar, plane_bytes * (VALIDATE ? 3u : 2u) * (uint32_t)ng);
+    for (int g = 0; g < ng; g++) {
+      const size_t off = (size_t)(env_first + g) * p.Rp * CAP;
+      bulk_load(s.xs + g * p.R * CAP, p.x + off, plane_bytes, s.mbar);
+      bulk_load(s.vs + g * p.R * CAP, p.v + off, plane_bytes, s.mbar);
+      if (VALIDATE) bulk_load(s.ws + g * p.R * CAP, p.w + off, plane_bytes, s.mbar);
+    }
   }
-  for (int i = tid; i < p.I; i += blockDim.x) {
-    // phase / elapsed update of the first tick (traffic_env.py:225-232); later ticks of the same
-    // actor step repeat the same action and are derived in closed form below.
-    int ph = p.phase[(size_t)env * p.I + i] != 0;
-    const int act = p.actions[(size_t)env * p.I + i] != 0;
-    int el = p.elapsed[(size_t)env * p.I + i];
-    int change;
-    if (learn_switch) { change = act; ph ^= act; } else { change = ph ^ act; ph = act; }
-    el = (el + 1) * (change ? 0 : 1);
-    s.phase[i] = (uint8_t)ph; s.act[i] = (uint8_t)act; s.elapsed[i] = el;
-    s.pdst[i] = p.passed_dst[(size_t)env * p.I + i]; s.ovf[i] = 0;
+  if (tid == 0) { s.misc[0] = nactive; s.misc[1] = -1; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; s.misc[6] = 0; }
+  if (tid < G) {
+    envm[ENVM_WORDS * tid + ENVM_OVF] = NO_OVERFLOW; envm[ENVM_WORDS * tid + ENVM_ORD] = -1; envm[ENVM_WORDS * tid + ENVM_TB] = 0;
+    envm[ENVM_WORDS * tid + ENVM_SKIP] = (tid >= ng) || (p.env_mask && p.env_mask[env_first + tid] == 0);
   }
-  if (tid == 0) { s.misc[0] = 0x7fffffff; s.misc[1] = -1; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; s.misc[6] = 0; }
-  if (warp == 0) {
-    // arrivals of the K ticks as per-tick, per-entry-road counts (cars are identical, so the
-    // order of arrivals within a tick only matters per road, where it is preserved)
-    const int ncnt = p.K * p.n_entry;
-    for (int i = lane; i < ncnt; i += 32) s.cnt[i] = 0;
+  for (int g = warp; g < ng; g += nwarps) {
+    // arrivals of the KT ticks of env g as per-tick, per-entry-road counts (cars are identical, so the
+    // order of arrivals within a tick only matters per road, where it is preserved); one warp per env
+    const int env = env_first + g;
+    uint8_t *const cntg = s.cnt + g * cnt_stride;
+    uint32_t *const snapg = snap_base + g * 2 * (KT + 1);
+    const EnvScalars *esg = p.env + env;
+    for (int i = lane; i < cnt_stride; i += 32) cntg[i] = 0;
     __syncwarp();
     if (p.arrival_mode == ARR_INJECTED) {
-      const long long cur = es->sched_cursor;
-      for (int t = lane; t < p.K; t += 32) {
+      const long long cur = esg->sched_cursor;
+      for (int t = lane; t < KT; t += 32) {
         const long long tick = cur + t - p.sched_first;
         if (tick >= 0 && tick < p.horizon) {
           const long long *off = p.sched_off + (size_t)env * (p.horizon + 1) + tick;
           for (long long k = off[0]; k < off[1]; k++) {
             const int idx = p.entry_idx[p.sched_roads[k]];
-            if (idx >= 0 && s.cnt[t * p.n_entry + idx] < 255) s.cnt[t * p.n_entry + idx]++;
+            if (idx >= 0 && cntg[t * p.n_entry + idx] < 255) cntg[t * p.n_entry + idx]++;
           }
         }
       }
     } else if (p.arrival_mode == ARR_PHILOX) {
       // The gap process is sequential (k empty ticks, a car, a new gap ...) but its draws are counter-based:
       // draw d arrives at tick skip0 + sum of the gaps of the draws before it.  32 draws per round, one per
-      // lane, exclusive prefix sum of the gaps, until a draw lands past the K ticks of this launch.
+      // lane, exclusive prefix sum of the gaps, until a draw lands past the KT ticks of this launch.
       // snap[T] = (draw, skip) state after T ticks, written by the lane whose car is the next one due.
-      uint32_t draw0 = es->ph_draw;
-      long long tbase = es->ph_skip;          // arrival tick of draw `draw0`
+      uint32_t draw0 = esg->ph_draw;
+      long long tbase = esg->ph_skip;         // arrival tick of draw `draw0`
       long long prev = 0;                     // arrival tick of the draw before draw0 (ticks <= prev are settled)
       const uint32_t k0 = p.seed, k1 = (uint32_t)(p.env_id_base + env);
-      if (lane == 0) { s.snap[0] = draw0; s.snap[1] = (uint32_t)tbase; }
+      if (lane == 0) { snapg[0] = draw0; snapg[1] = (uint32_t)tbase; }
       for (;;) {
         uint32_t o[4];
         philox4x32_10(draw0 + lane, 0, 0, 0, k0, k1, o);
@@ -358,44 +401,69 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         const long long tick = tbase + incl - gap;              // arrival tick of my draw
         long long before = __shfl_up_sync(FULL, tick, 1);
         if (lane == 0) before = prev;
-        if (tick < p.K) {
+        if (tick < KT) {
           // 8-bit count per (tick, entry road), four to a word; bumped with a CAS so that a 256th arrival saturates
           // (and is reported through te_stats.arrival_saturations) instead of carrying into the neighbouring count
           const int idx = (int)__umulhi(o[1], (uint32_t)p.n_entry) + (int)tick * p.n_entry;
-          unsigned int *wp = reinterpret_cast<unsigned int *>(s.cnt) + (idx >> 2);
+          unsigned int *wp = reinterpret_cast<unsigned int *>(cntg) + (idx >> 2);
           const int sh = (idx & 3) * 8;
           unsigned int seen = *wp;
           for (;;) {
             if (((seen >> sh) & 0xffu) == 0xffu) { atomicAdd(&p.stats->arrival_saturations, 1ull); break; }
-            const unsigned int prev = atomicCAS(wp, seen, seen + (1u << sh));
-            if (prev == seen) break;
-            seen = prev;
+            const unsigned int prevw = atomicCAS(wp, seen, seen + (1u << sh));
+            if (prevw == seen) break;
+            seen = prevw;
           }
         }
-        // after T ticks, for before < T <= tick (and T <= K), my draw is the next car: skip = tick - T
-        for (long long T = (before + 1 > 1 ? before + 1 : 1); T <= tick && T <= p.K; T++) {
-          s.snap[2 * T] = draw0 + lane; s.snap[2 * T + 1] = (uint32_t)(tick - T);
+        // after T ticks, for before < T <= tick (and T <= KT), my draw is the next car: skip = tick - T
+        for (long long T = (before + 1 > 1 ? before + 1 : 1); T <= tick && T <= KT; T++) {
+          snapg[2 * T] = draw0 + lane; snapg[2 * T + 1] = (uint32_t)(tick - T);
         }
         const long long last = __shfl_sync(FULL, tick, 31);
         const long long next_base = __shfl_sync(FULL, tbase + incl, 31);
-        if (last >= p.K) break;
+        if (last >= KT) break;
         draw0 += 32; tbase = next_base; prev = last;
       }
     }
   }
-  __syncthreads();
+  __syncthreads();       // (the mbarrier is initialised for everybody)
   mbar_wait(s.mbar, 0);  // the ring planes have landed
-  if (tid >= p.R) {      // a padding row: an empty ring behind a free road, like te_reset leaves one
+  for (int i = tid; i < nI; i += blockDim.x) {
+    // phase / elapsed update of the first tick (traffic_env.py:225-232); later ticks of the launch
+    // repeat the same action and are derived in closed form below.
+    int ph = p.phase[ibase + i] != 0;
+    int act;
+    if (p.controller == CTRL_GREEDY) {
+      // algorithms/greedy.py:14-16: cars_on_roads()[row, col, :] . [1, 1, -1, -1] < 0 from the ring indices as staged
+      const int g = i / p.I, ii = i - g * p.I;
+      int bal = 0;
+      for (int dd = 0; dd < 4; dd++) {
+        const uint32_t w0 = __float_as_uint(s.xs[(g * p.R + dd * p.V + ii) * CAP]);
+        const int cn = ring_count(w0 & 0xff, (w0 >> 8) & 0xff);
+        bal += dd < 2 ? cn : -cn;
+      }
+      act = bal < 0;
+      if (p.actions_out) p.actions_out[ibase + i] = (uint8_t)act;
+    } else {
+      act = p.actions[ibase + i] != 0;
+    }
+    int el = p.elapsed[ibase + i];
+    int change;
+    if (learn_switch) { change = act; ph ^= act; } else { change = ph ^ act; ph = act; }
+    el = (el + 1) * (change ? 0 : 1);
+    s.phase[i] = (uint8_t)ph; s.act[i] = (uint8_t)act; s.elapsed[i] = el;
+    s.pdst[i] = p.passed_dst[ibase + i]; s.ovf[i] = 0;
+  }
+  if (tid >= nrows) {    // a padding row: an empty ring behind a free road, like te_reset leaves one
     s.xs[tid * CAP] = __uint_as_float(pack_meta(1, 1, 0)); s.vs[tid * CAP] = __int_as_float(0);
     s.xs[tid * CAP + 1] = INF; s.vs[tid * CAP + 1] = 0.f;
   }
 
-  // ---- road -> (warp, lane) assignment for this launch, balanced by car count: counting sort of the roads by
+  // ---- row -> (warp, lane) assignment for this launch, balanced by car count: counting sort of the rows by
   // their current number of cars (0..18), then dealt to the warps in snake order, so every warp simulates
   // nearly the same number of cars per tick and the two CTA barriers of a tick wait on even warps.
   // Any bijection gives the same results (the update is per car); only the waiting changes.
-  const int nwarps = blockDim.x >> 5;            // blockDim.x == Rp
-  int my_road;
+  int my_sr;
   {
     int *hist = s.wait;                                      // [0..19] counts, [20..39] tickets (idle until the epilogue)
     short *owner = reinterpret_cast<short *>(s.meta);        // idle until the tick loop
@@ -406,20 +474,24 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     atomicAdd(&hist[n0], 1);
     __syncthreads();
     int base = 0;
-    for (int c2 = RING - 1; c2 > n0; --c2) base += hist[c2];  // roads with more cars come first
+    for (int c2 = RING - 1; c2 > n0; --c2) base += hist[c2];  // rows with more cars come first
     const int rank = base + atomicAdd(&hist[20 + n0], 1);
     const int row = rank / nwarps, pos = rank - row * nwarps;
     const int w = (row & 1) ? nwarps - 1 - pos : pos;
     owner[w * 32 + row] = (short)tid;
     __syncthreads();
-    my_road = owner[tid];
+    my_sr = owner[tid];
     __syncthreads();                                         // the scratch regions are reused below
   }
   // ---- lane = road: ring indices, counters and topology of my road live in registers
-  const bool is_road = my_road < p.R, is_train = my_road < p.r;
-  float *xr = s.xs + my_road * CAP, *vr = s.vs + my_road * CAP;
-  float *wr = VALIDATE ? s.ws + my_road * CAP : nullptr;
-  const float steps0 = es->steps;  // np.float32 tick counter at the start of this launch (small integer: exact)
+  const bool is_road = my_sr < nrows;
+  const int my_g = (GROUPED && is_road) ? my_sr / p.R : 0;   // env of my road within the CTA
+  const int my_road = GROUPED ? (is_road ? my_sr - my_g * p.R : p.R) : my_sr;   // road index inside its env (padding rows: >= R)
+  const bool is_train = my_road < p.r;
+  float *xr = s.xs + my_sr * CAP, *vr = s.vs + my_sr * CAP;
+  float *wr = VALIDATE ? s.ws + my_sr * CAP : nullptr;
+  const float steps0 = p.env[env_first + my_g].steps;  // np.float32 tick counter at the start of this launch (small integer: exact)
+  const int emi = ENVM_WORDS * my_g;                         // my env's words inside envm
   int ld, lc, wait, det, passed = 0;
   float leadx;
   {
@@ -427,13 +499,23 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     ld = w0 & 0xff; lc = (w0 >> 8) & 0xff; det = (w0 >> 16) & 0xff;
     wait = __float_as_int(vr[0]);
     leadx = xr[ld];
-    s.tailx[my_road] = (lc != ld) ? xr[lc] : INF;
+    s.tailx[my_sr] = (lc != ld) ? xr[lc] : INF;
   }
-  const int nxt = p.nexts[my_road], upr = p.up[my_road], ei = p.entry_idx[my_road];
-  const int dst = is_train ? my_road % p.V : 0;
+  // topology in row (super-road) indices; -1 = none
+  int nxt = -1, upr = -1, ei = -1;
+  if (!GROUPED || is_road) {   // (one env per CTA: the topology tables are padded like the CTA, -1 in padding rows)
+    nxt = p.nexts[my_road]; upr = p.up[my_road]; ei = p.entry_idx[my_road];
+    if (GROUPED) {
+      if (nxt >= 0) nxt += my_g * p.R;
+      if (upr >= 0) upr += my_g * p.R;
+      if (ei >= 0) ei += my_g * cnt_stride;                  // index of my entry road's tick-0 arrival count inside s.cnt
+    }
+  }
+  const int dst = is_train ? my_g * p.I + my_road % p.V : 0;
   // update_lights (traffic_env.py:81-94) in closed form: within one launch the action is constant, so the approach
-  // is blocked (red or yellow) at tick t  <=>  t < ylim.  learn_switch with a set action toggles every tick, which
-  // keeps elapsed at 0 (always yellow); otherwise phase_t is constant and elapsed_t = elapsed_0 + t.
+  // is blocked (red or yellow) at tick tt of the launch  <=>  tt < ylim.  learn_switch with a set action toggles every
+  // tick, which keeps elapsed at 0 (always yellow); otherwise phase is constant and elapsed = elapsed_0 + tt.  (A new
+  // actor step with the same action changes nothing: its first tick finds phase == action.)
   int ylim = 0;
   if (is_train) {
     const bool ls_act = learn_switch && s.act[dst];
@@ -447,29 +529,43 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   unsigned int *wcnt = reinterpret_cast<unsigned int *>(rt + 32);        // waiting | detected << 16 per listed road
   unsigned short *wst = reinterpret_cast<unsigned short *>(wcnt + 32);   // first list position of each listed road
   const uint32_t rt_a = smem_u32(rt), wcnt_a = smem_u32(wcnt);
-  const uint32_t xrow_a = smem_u32(xr);                                  // shared address of x[my_road][0]
+  const uint32_t xrow_a = smem_u32(xr);                                  // shared address of x[my row][0]
   constexpr int VOFF = L.vs - L.xs;                                      // v plane relative to the x plane
   const unsigned lt_mask = (1u << lane) - 1u;
   __syncthreads();
 
   const IdmConst c = p.idm;
+  const int obs_f_len = 2 * p.r + p.I, obs_i_len = 2 * p.r + 2 * p.I;
+  const bool clear_remi = !p.raw && (p.flags & F_REMI);
+  const bool use_wire = !p.raw && p.wire;
+  // a row that never takes part: padding, or a road of an env that is not stepped (env_mask)
+  const bool out_of_play = GROUPED ? (!is_road || envm[emi + ENVM_SKIP] != 0) : false;
   int veh_local = 0, gen_local = 0, exit_local = 0;
-  int t = 0;
-  for (; t < p.K; t++) {
+  int tb = 0;            // ticks my env ran in the earlier actor steps of this launch (te_step_multi)
+
+  for (int step = 0;; step++) {
+  // A lane takes part in a tick while its env is still running: an env whose ring overflowed in tick t stops after t
+  // (Repeater: `if done: break`, traffic_test.py:55) while the other envs of the CTA carry on; padding rows never run.
+  // (One env per CTA: never frozen - padding rows are empty rings with no topology, and the loop simply ends.)
+  bool frozen = out_of_play;
+  for (int t = 0; t < p.K; t++) {
+    const int tt = tb + t;     // tick of the launch for my env: arrival-process tick, light clock, birth stamp
+    const int gt = step * p.K + t;   // CTA-wide tick counter of the launch: stamps the ordered-transfer requests, which are
+                                     // raised before the first barrier of a tick and therefore never reset
     // ---------------------------------------------------------------- phase A
     int dropped = 0;
-    if (ei >= 0) {  // entry arrivals, traffic_env.py:274-283
-      const int na = s.cnt[t * p.n_entry + ei];
+    if (ei >= 0 && !frozen) {  // entry arrivals, traffic_env.py:274-283
+      const int na = s.cnt[ei + tt * p.n_entry];
       for (int k = 0; k < na; k++) {
         gen_local++;
-        if (!ring_push(xr, vr, wr, ld, lc, c.x_new, c.v_new, steps0 + (float)t, c)) dropped++;  // car[wi] = tick, :279
+        if (!ring_push(xr, vr, wr, ld, lc, c.x_new, c.v_new, steps0 + (float)tt, c)) dropped++;  // car[wi] = tick, :279
       }
     }
-    if (is_train) {  // update_lights
-      if (t < ylim) leadx = p.length;
+    if (is_train && !frozen) {  // update_lights
+      if (tt < ylim) leadx = p.length;
       else leadx = nxt >= 0 ? __fadd_rn(s.tailx[nxt], p.length) : INF;
     }
-    const int n = ring_count(ld, lc);
+    const int n = frozen ? 0 : ring_count(ld, lc);
     // The warp's live cars, road after road in ring order, form one list of `total` cars; lane l simulates the
     // q = ceil(total / 32) consecutive cars [l q, l q + q).  A car's leader is the list entry before it (or the
     // road's virtual leader), so a lane keeps the leader's PRE-update (x, v) in registers from its previous
@@ -519,7 +615,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           float xn = lds_f32(addr), vn = lds_f32_off<VOFF>(addr);
           const float xl = px, vl = pv, ll = pl;
           px = xn; pv = vn; pl = c.len;
-          idm_update(c, s.tabs, xl, vl, ll, xn, vn);
+          idm_update<FA>(c, p.idm_g, s.tabs, xl, vl, ll, xn, vn);
           sts_f32(addr, xn); sts_f32_off<VOFF>(addr, vn);
           // wrapped ring, low segment (slot < leading): the reference tests x, not v (traffic_env.py:210).
           // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
@@ -557,7 +653,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         f = f2; npop++;
       }
       if (npop > 0) {
-        if (VALIDATE && nxt < 0 && is_road) {
+        if (VALIDATE && nxt < 0) {
           // advance_hack, traffic_env.py:153-154: trip time of every car that leaves the map
           const unsigned long long base = atomicAdd(p.trip_count, (unsigned long long)npop);
           int fs = ld;
@@ -565,9 +661,9 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
             fs = ring_wrap(fs + 1);
             if ((long long)(base + k) < p.trip_cap) {
               TripRecord rec;
-              rec.env = env;
-              rec.trip = __fsub_rn(steps0 + (float)t, wr[fs]) / 2.0f;
-              rec.order = (((unsigned long long)(es->sched_cursor + t)) << 24) | ((unsigned long long)my_road << 8) | (unsigned)k;
+              rec.env = env_first + my_g;
+              rec.trip = __fsub_rn(steps0 + (float)tt, wr[fs]) / 2.0f;
+              rec.order = (((unsigned long long)(p.env[env_first + my_g].sched_cursor + tt)) << 24) | ((unsigned long long)my_road << 8) | (unsigned)k;
               p.trips[base + k] = rec;
             }
           }
@@ -579,136 +675,194 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           s.pdst[dst] = 1;                              // :128
           // Two or more pops while the upstream road has a higher index: its insert (which in the
           // reference runs after these pops were consumed) could reuse the slots the popped cars
-          // still occupy.  Run this tick's transfers in strict road order instead.
-          if (npop >= 2 && upr > my_road) s.misc[1] = t;
+          // still occupy.  Run this tick's transfers of this env in strict road order instead.
+          if (npop >= 2 && upr > my_sr) { envm[emi + ENVM_ORD] = gt; s.misc[1] = gt; }
         }
       }
     }
-    s.meta[my_road] = (uint32_t)ld | ((uint32_t)lc << 8) | ((uint32_t)ld_pre << 16) | ((uint32_t)npop << 24);
+    s.meta[my_sr] = (uint32_t)ld | ((uint32_t)lc << 8) | ((uint32_t)ld_pre << 16) | ((uint32_t)npop << 24);
     __syncthreads();
     // ---------------------------------------------------------------- phase C
-    if (s.misc[1] == t || (p.flags & F_ORDERED)) {
-      if (tid == 0) {
-        for (int e = 0; e < p.R; e++) {
-          const int d = p.nexts[e];
-          if (d < 0 || (s.meta[e] >> 24) == 0) continue;
-          const uint32_t md = s.meta[d];
-          int dlc = (md >> 8) & 0xff;
-          const int chk = (e < d) ? (md >> 16) & 0xff : md & 0xff;
-          const int dr = transfer(p, s, e, d, chk, dlc, VALIDATE);
-          s.meta[d] = (md & 0xffff00ffu) | ((uint32_t)dlc << 8);
-          if (dr) { if (d < p.r) s.ovf[d % p.V] += dr; s.misc[3] += dr; if (s.misc[0] > t) s.misc[0] = t; }
+    const bool want_parallel = !frozen && upr >= 0 && (s.meta[upr] >> 24) != 0;
+    if (s.misc[1] == gt || (p.flags & F_ORDERED)) {      // (CTA-uniform) some env of the CTA needs ordered transfers
+      const bool ord_env = !frozen && (GROUPED ? is_road : true) && (envm[emi + ENVM_ORD] == gt || (p.flags & F_ORDERED));
+      if (ord_env) {
+        if (my_road == 0) {                              // one lane per env walks its roads in the reference's order
+          const int row0 = my_g * p.R;
+          int dr_total = 0;
+          for (int e = 0; e < p.R; e++) {
+            const int d = p.nexts[e];
+            if (d < 0 || (s.meta[row0 + e] >> 24) == 0) continue;
+            const uint32_t md = s.meta[row0 + d];
+            int dlc = (md >> 8) & 0xff;
+            const int chk = (e < d) ? (md >> 16) & 0xff : md & 0xff;
+            const int dr = transfer(p, s, row0 + e, row0 + d, chk, dlc, VALIDATE);
+            s.meta[row0 + d] = (md & 0xffff00ffu) | ((uint32_t)dlc << 8);
+            if (dr) { if (d < p.r) atomicAdd(&s.ovf[my_g * p.I + d % p.V], dr); dr_total += dr; }
+          }
+          if (dr_total) {
+            atomicAdd(&s.misc[3], dr_total);
+            if (atomicMin(&envm[emi + ENVM_OVF], t) == NO_OVERFLOW) atomicSub(&s.misc[0], 1);
+          }
+          atomicAdd(&s.misc[5], 1);
         }
-        s.misc[5] += 1;
+      } else if (want_parallel) {
+        dropped += transfer(p, s, upr, my_sr, (upr < my_sr) ? ld_pre : ld, lc, VALIDATE);
       }
       __syncthreads();
-      lc = (s.meta[my_road] >> 8) & 0xff;
-    } else if (is_road && upr >= 0 && (s.meta[upr] >> 24) != 0) {
-      dropped += transfer(p, s, upr, my_road, (upr < my_road) ? ld_pre : ld, lc, VALIDATE);
+      if (ord_env) lc = (s.meta[my_sr] >> 8) & 0xff;
+    } else if (want_parallel) {
+      dropped += transfer(p, s, upr, my_sr, (upr < my_sr) ? ld_pre : ld, lc, VALIDATE);
     }
     if (dropped) {  // OVERFLOW_PENALTY on the road's intersection, traffic_env.py:109-111; done
       if (is_train) atomicAdd(&s.ovf[dst], dropped);
       atomicAdd(&s.misc[3], dropped);
-      atomicMin(&s.misc[0], t);
+      if (atomicMin(&envm[emi + ENVM_OVF], t) == NO_OVERFLOW) atomicSub(&s.misc[0], 1);   // the first overflow of this env: it stops after this tick
     }
-    s.tailx[my_road] = (lc != ld) ? xr[lc] : INF;
+    s.tailx[my_sr] = (lc != ld) ? xr[lc] : INF;
     __syncthreads();
-    if (s.misc[0] <= t) { t++; break; }  // Repeater: `if done: break` (traffic_test.py:55)
+    // tick-stamped (a fast warp that has already flagged tick t + 1 cannot be mistaken for tick t)
+    if (GROUPED) {
+      frozen = frozen || envm[emi + ENVM_OVF] <= t;
+      if (s.misc[0] <= 0) break;  // every env of the CTA has stopped
+    } else if (envm[ENVM_OVF] <= t) break;
   }
-  const int ticks_run = t;  // >= 1
-  const int last = ticks_run - 1;
 
-  // ------------------------------------------------------------ epilogue
-  for (int o = 16; o > 0; o >>= 1) {
-    veh_local += __shfl_xor_sync(FULL, veh_local, o);
-    gen_local += __shfl_xor_sync(FULL, gen_local, o);
-    exit_local += __shfl_xor_sync(FULL, exit_local, o);
-  }
-  if (lane == 0) { atomicAdd(&s.misc[2], veh_local); atomicAdd(&s.misc[4], gen_local); atomicAdd(&s.misc[6], exit_local); }
-  s.wait[my_road] = wait;
+  // ------------------------------------------------------------ end of the actor step: observation, reward, done
+  const bool last_step = step + 1 >= p.nsteps;
+  s.wait[my_sr] = wait;
   __syncthreads();
-
-  const int obs_f_len = 2 * p.r + p.I, obs_i_len = 2 * p.r + 2 * p.I;
-  const bool clear_remi = !p.raw && (p.flags & F_REMI);
-  unsigned char *wire_rec = (!p.raw && p.wire) ? p.wire + (size_t)env * p.wire_stride : nullptr;
-  // final light state after `ticks_run` ticks, reward
-  for (int i = tid; i < p.I; i += blockDim.x) {
+  {
+    const int ov = envm[emi + ENVM_OVF];
+    tb += (ov != NO_OVERFLOW) ? ov + 1 : p.K;     // ticks my env has run so far in this launch
+  }
+  const size_t step_env0 = (size_t)step * p.num_envs;      // outputs of actor step j: j * num_envs env slots further on
+  // final light state after the ticks each env ran, reward
+  for (int i = tid; i < nI; i += blockDim.x) {
+    const int g = i / p.I, ii = i - g * p.I;
+    if (GROUPED && envm[ENVM_WORDS * g + ENVM_SKIP]) continue;
+    const int env = env_first + g;
+    const int ov = envm[ENVM_WORDS * g + ENVM_OVF];
+    const int last = envm[ENVM_WORDS * g + ENVM_TB] + ((ov != NO_OVERFLOW) ? ov : p.K - 1);   // the last tick of the launch env g ran
+    unsigned char *wire_rec = use_wire ? p.wire + (step_env0 + env) * p.wire_stride : nullptr;
     const bool ls_act = learn_switch && s.act[i];
     const int ph_f = s.phase[i] ^ (ls_act ? (last & 1) : 0);
     const int el_f = ls_act ? 0 : s.elapsed[i] + last;
-    p.phase[(size_t)env * p.I + i] = (uint8_t)ph_f;
-    p.elapsed[(size_t)env * p.I + i] = el_f;
+    if (last_step) {
+      p.phase[ibase + i] = (uint8_t)ph_f;
+      p.elapsed[ibase + i] = el_f;
+    }
     float rew = (float)(-10 * s.ovf[i]);  // OVERFLOW_PENALTY summed over the ticks: small integers, exact, +0 when none
     if (clear_remi) {
-      // remi, traffic_env.py:64-78, over the 4 approaches of intersection i in road order
+      // remi, traffic_env.py:64-78, over the 4 approaches of intersection ii in road order
       rew = 0.f;
       const bool pd = s.pdst[i] != 0;
       for (int dd = 0; dd < 4; dd++) {
-        const int e = dd * p.V + i;
+        const int e = g * p.R + dd * p.V + ii;
         const bool green = ((dd < 2) ? 1 : 0) != ph_f;
         const bool w = s.wait[e] > 0;
         if (w && !green && !pd) rew = __fsub_rn(rew, 0.5f);
         else if (pd && green && !w) rew = __fadd_rn(rew, 0.5f);
       }
+      s.pdst[i] = 0;
     }
-    p.passed_dst[(size_t)env * p.I + i] = clear_remi ? 0 : s.pdst[i];
+    if (last_step) p.passed_dst[ibase + i] = s.pdst[i];
     if (p.raw) {
-      p.reward[(size_t)env * p.I + i] = rew;
-      p.obs_i[(size_t)env * obs_i_len + 2 * p.r + i] = ph_f;
-      p.obs_i[(size_t)env * obs_i_len + 2 * p.r + p.I + i] = el_f;
+      p.reward[ibase + i] = rew;
+      p.obs_i[(size_t)env * obs_i_len + 2 * p.r + ii] = ph_f;
+      p.obs_i[(size_t)env * obs_i_len + 2 * p.r + p.I + ii] = el_f;
     } else {
       // Repeater: obs[-I:] / 100 * (2 * phase - 1): int32 / int -> float64, cast to float32 on store
       const float light = __double2float_rn(__dmul_rn(__ddiv_rn((double)el_f, 100.0), (double)(2 * ph_f - 1)));
       if (wire_rec) {
-        reinterpret_cast<float *>(wire_rec + 2 * p.r)[i] = light;
-        reinterpret_cast<float *>(wire_rec + 2 * p.r + 4 * p.I)[i] = rew;
+        reinterpret_cast<float *>(wire_rec + 2 * p.r)[ii] = light;
+        reinterpret_cast<float *>(wire_rec + 2 * p.r + 4 * p.I)[ii] = rew;
       } else {
-        p.reward[(size_t)env * p.I + i] = rew;
-        p.obs_f[(size_t)env * obs_f_len + 2 * p.r + i] = light;
+        p.reward[step_env0 * p.I + ibase + i] = rew;
+        p.obs_f[(step_env0 + env) * obs_f_len + 2 * p.r + ii] = light;
       }
     }
-    s.ovf[i] = __float_as_int(rew);  // reuse: reward for the return statistic below
+    s.rew[i] = rew;     // for the return statistic below
+    s.ovf[i] = 0;       // penalties of the next actor step start from zero
   }
-  if (is_train) {
+  if (is_train && !out_of_play) {
+    const int env = env_first + my_g;
     if (p.raw) {
       p.obs_i[(size_t)env * obs_i_len + my_road] = passed;
       p.obs_i[(size_t)env * obs_i_len + p.r + my_road] = det;
-    } else if (wire_rec) {
+    } else if (use_wire) {
+      unsigned char *wire_rec = p.wire + (step_env0 + env) * p.wire_stride;
       wire_rec[my_road] = (unsigned char)passed;
       wire_rec[p.r + my_road] = (unsigned char)det;
     } else {
-      p.obs_f[(size_t)env * obs_f_len + my_road] = (float)passed;
-      p.obs_f[(size_t)env * obs_f_len + p.r + my_road] = (float)det;
+      p.obs_f[(step_env0 + env) * obs_f_len + my_road] = (float)passed;
+      p.obs_f[(step_env0 + env) * obs_f_len + p.r + my_road] = (float)det;
     }
+    passed = 0;                     // Repeater starts the next actor step from zero (traffic_test.py:40)
+    if (clear_remi) wait = 0;       // remi clears `waiting` (traffic_env.py:77)
   }
-  // pack ring indices back into the row headers, restore the virtual leader's x, flush
-  xr[ld] = leadx;
-  xr[0] = __uint_as_float(pack_meta(ld, lc, det));
-  vr[0] = __int_as_float((clear_remi || !is_train) ? 0 : wait);
-  fence_proxy_async();  // my generic-proxy writes to the planes become visible to the bulk-copy engine
+  if (last_step) {
+    for (int o = 16; o > 0; o >>= 1) {
+      veh_local += __shfl_xor_sync(FULL, veh_local, o);
+      gen_local += __shfl_xor_sync(FULL, gen_local, o);
+      exit_local += __shfl_xor_sync(FULL, exit_local, o);
+    }
+    if (lane == 0) { atomicAdd(&s.misc[2], veh_local); atomicAdd(&s.misc[4], gen_local); atomicAdd(&s.misc[6], exit_local); }
+  }
+  if (last_step && !out_of_play) {
+    // pack ring indices back into the row headers, restore the virtual leader's x (then: flush)
+    xr[ld] = leadx;
+    xr[0] = __uint_as_float(pack_meta(ld, lc, det));
+    vr[0] = __int_as_float(is_train ? wait : 0);
+    fence_proxy_async();  // my generic-proxy writes to the planes become visible to the bulk-copy engine
+  }
   __syncthreads();
-  if (tid == 0) {
-    bulk_store(p.x + (size_t)env * p.Rp * CAP, s.xs, plane_bytes);
-    bulk_store(p.v + (size_t)env * p.Rp * CAP, s.vs, plane_bytes);
-    if (VALIDATE) bulk_store(p.w + (size_t)env * p.Rp * CAP, s.ws, plane_bytes);
-  }
-  if (tid == 0) {
-    const bool overflowed = s.misc[0] != 0x7fffffff;
-    if (wire_rec) wire_rec[2 * p.r + 8 * p.I] = overflowed ? 1 : 0;
-    else p.done[env] = overflowed ? 1 : 0;
-    es->steps = es->steps + (float)ticks_run;
-    es->sched_cursor += ticks_run;
-    if (p.arrival_mode == ARR_PHILOX) { es->ph_draw = s.snap[2 * ticks_run]; es->ph_skip = s.snap[2 * ticks_run + 1]; }
+  if (tid < ng && !envm[ENVM_WORDS * tid + ENVM_SKIP]) {          // thread g: the scalars of env g for this actor step
+    const int g = tid, env = env_first + g;
+    const int ov = envm[ENVM_WORDS * g + ENVM_OVF];
+    const bool overflowed = ov != NO_OVERFLOW;
+    const int ticks_run = overflowed ? ov + 1 : p.K;   // >= 1
+    const int ticks_total = envm[ENVM_WORDS * g + ENVM_TB] + ticks_run;   // ticks env g has run in this launch
+    EnvScalars *esg = p.env + env;
+    if (use_wire) p.wire[(step_env0 + env) * p.wire_stride + 2 * p.r + 8 * p.I] = overflowed ? 1 : 0;
+    else p.done[step_env0 + env] = overflowed ? 1 : 0;
     if (!p.raw) {
       double mean = 0.0;
-      for (int i = 0; i < p.I; i++) mean += (double)__int_as_float(s.ovf[i]);
+      for (int i = 0; i < p.I; i++) mean += (double)s.rew[g * p.I + i];
       mean /= (double)p.I;
-      es->ep_ret += mean; es->ep_disc += es->ep_mult * mean; es->ep_mult *= (double)p.gamma;
-      es->ep_step += 1;
-      es->done = overflowed ? 1 : 0;
-      atomicAdd(&p.stats->actor_steps, 1ull);
+      const double mult = esg->ep_mult;
+      esg->ep_ret += mean; esg->ep_disc += mult * mean; esg->ep_mult = mult * (double)p.gamma;
     }
-    atomicAdd(&p.stats->ticks, (unsigned long long)ticks_run);
+    if (last_step) {
+      esg->steps = esg->steps + (float)ticks_total;
+      esg->sched_cursor += ticks_total;
+      if (p.arrival_mode == ARR_PHILOX) {
+        const uint32_t *snapg = snap_base + g * 2 * (KT + 1);
+        esg->ph_draw = snapg[2 * ticks_total]; esg->ph_skip = snapg[2 * ticks_total + 1];
+      }
+      if (!p.raw) {
+        esg->ep_step += p.nsteps;
+        esg->done = overflowed ? 1 : 0;
+        atomicAdd(&p.stats->actor_steps, (unsigned long long)p.nsteps);
+      }
+      atomicAdd(&p.stats->ticks, (unsigned long long)ticks_total);
+    } else {   // re-arm the stamps of env g for the next actor step
+      envm[ENVM_WORDS * g + ENVM_TB] = ticks_total;
+      envm[ENVM_WORDS * g + ENVM_OVF] = NO_OVERFLOW;   // (raised only after the first barrier of a tick: safe to reset here)
+    }
+  }
+  if (last_step) break;
+  if (tid == 0) s.misc[0] = nactive;   // (decremented only after the first barrier of a tick: safe to reset here)
+  }
+
+  // ------------------------------------------------------------ flush
+  if (tid == 0) {
+    for (int g = 0; g < ng; g++) {
+      const size_t off = (size_t)(env_first + g) * p.Rp * CAP;
+      bulk_store(p.x + off, s.xs + g * p.R * CAP, plane_bytes);
+      bulk_store(p.v + off, s.vs + g * p.R * CAP, plane_bytes);
+      if (VALIDATE) bulk_store(p.w + off, s.ws + g * p.R * CAP, plane_bytes);
+    }
     atomicAdd(&p.stats->vehicle_updates, (unsigned long long)s.misc[2]);
     if (s.misc[3]) atomicAdd(&p.stats->overflows, (unsigned long long)s.misc[3]);
     atomicAdd(&p.stats->cars_generated, (unsigned long long)s.misc[4]);
@@ -836,18 +990,19 @@ __global__ void te_test_powf_kernel(const float *x, float y, float *out, long lo
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = powf_glibc(x[i], y, &g_powf_tables);
 }
-__global__ void te_test_idm_kernel(IdmConst c, const float *xl, const float *vl, const float *ll, const float *x,
+__global__ void te_test_idm_kernel(IdmConst c, const IdmConst *cg, const float *xl, const float *vl, const float *ll, const float *x,
                                    const float *v, float *xo, float *vo, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float xx = x[i], vv = v[i];
-    idm_update(c, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
+    if (c.pow2 && c.delta_is_four) idm_update<true>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
+    else idm_update<false>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
     xo[i] = xx; vo[i] = vv;
   }
 }
 // Arithmetic-only ceiling: every lane runs `iters` dependent IDM updates of one car behind a leader that
 // drives at constant speed (registers only, full-precision path: both divisions and powf every time).
-__global__ void te_idm_peak_kernel(IdmConst c, int iters, float *sink) {
+__global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, float *sink) {
   __shared__ PowfTables tabs;
   for (int i = threadIdx.x; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long *>(&tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
@@ -857,7 +1012,7 @@ __global__ void te_idm_peak_kernel(IdmConst c, int iters, float *sink) {
   float xl = 30.f + 0.01f * (float)(gid & 255);
   const float vl = 9.f, step = __fmul_rn(vl, c.rate);
   for (int i = 0; i < iters; i++) {
-    idm_update(c, &tabs, xl, vl, c.len, x, v);
+    idm_update<false>(c, cg, &tabs, xl, vl, c.len, x, v);
     xl = __fadd_rn(xl, step);
   }
   sink[gid] = x + v;

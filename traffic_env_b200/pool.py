@@ -4,9 +4,13 @@ The reference's learners each own an env and step it from their own loop - A3C f
 Python threads (algorithms/a3c.py:66-72, 110-137; rollout contract `epoch`, :52-63), DQN / DRQN / PG from
 one loop (qlearn.py:97-104, qrnn.py:108-118, polgrad_rnn.py:6-15).  `EnvPool(num_slots).slot(i)` gives
 each of them an object with that single-env API (reset / step / action_space / observation_space /
-reward_size / unwrapped.cars_on_roads / unwrapped.graph) while the device advances every slot in ONE
-kernel launch per actor step: a step() call blocks until all slots that take part in the current round
-have submitted their action, the last one launches the batch, everyone gets their row.
+reward_size / unwrapped.cars_on_roads / unwrapped.graph) while the device advances the slots in batches.
+
+No slot waits for another slot's owner: a step() call queues its action; whichever caller finds no launch in
+flight becomes the leader, takes EVERY action queued so far (at least its own) and advances exactly those slots
+with one te_step_masked launch (the other slots' state and arrival streams are untouched); callers that arrive
+while a launch is in flight are served by the next one.  A slow learner thread therefore only delays itself, and
+the batch size adapts to how many threads are ready.
 
 Semantics per slot are those of Remi(Repeater(K)) on the reference env (traffic_test.py:27-64): reset() is
 TrafficEnv._reset followed by one step with a random action whose observation is returned (:34-36).
@@ -54,9 +58,11 @@ class EnvSlot(object):
     def unwrapped(self):
         return self
 
-    def reset(self):
-        self.pool._reset_slot(self.index)
-        return self.step(self.action_space.sample())[0]
+    def reset(self, init_phase=None, first_action=None):
+        """Repeater._reset (traffic_test.py:34-36): TrafficEnv._reset, then one step with a random action whose
+        observation is returned.  init_phase / first_action (extensions) replace the two random draws."""
+        self.pool._reset_slot(self.index, init_phase)
+        return self.step(self.action_space.sample() if first_action is None else first_action)[0]
 
     def step(self, action):
         return self.pool._submit(self.index, action)
@@ -74,54 +80,72 @@ class EnvPool(object):
         self.vec = VecTrafficEnv(num_envs=num_slots, **vec_kwargs)
         self.num_slots = num_slots
         self._cv = threading.Condition()
-        self._active = set(range(num_slots))      # slots whose owner is still stepping
-        self._pending = {}                        # slot -> action of the current round
-        self._round = 0
-        self._results = {}
+        self._pending = {}                        # slot -> action, queued for the next launch
+        self._results = {}                        # slot -> (obs, reward, done, info) of its last step, until fetched
+        self._launching = False
         self._actions = np.zeros((num_slots, self.vec.intersections), np.uint8)
+        self._mask = np.zeros(num_slots, np.uint8)
         self._slots = [EnvSlot(self, i) for i in range(num_slots)]
         self.launches = 0
+        self.stepped = 0                          # env actor steps served (sum of batch sizes)
 
     def slot(self, i):
         return self._slots[i]
 
     # ---- called by the slots
-    def _reset_slot(self, i):
+    def _reset_slot(self, i, init_phase=None):
         with self._cv:
+            while self._launching:                # the device state of slot i must not change under a launch
+                self._cv.wait()
             mask = np.zeros(self.num_slots, np.uint8)
             mask[i] = 1
-            phases = np.random.randint(2, size=(self.num_slots, self.vec.intersections))
+            phases = np.zeros((self.num_slots, self.vec.intersections), np.uint8)
+            phases[i] = np.random.randint(2, size=self.vec.intersections) if init_phase is None else np.asarray(init_phase).astype(bool)
             self.vec.reset(mask=mask, init_phase=phases)
 
     def _cars(self, i):
         with self._cv:
+            while self._launching:
+                self._cv.wait()
             return self.vec.cars_on_roads()[i].copy()
 
     def leave(self, i):
-        """The owner of slot i stops stepping (its env no longer gates the rounds)."""
+        """The owner of slot i stops stepping (kept for API compatibility: nobody waits for it anyway)."""
         with self._cv:
-            self._active.discard(i)
             self._pending.pop(i, None)
-            self._maybe_launch()
-
-    def _maybe_launch(self):
-        if self._active and set(self._pending) >= self._active:
-            for i, a in self._pending.items():
-                self._actions[i] = np.asarray(a).astype(bool).reshape(-1)
-            obs, rew, done = self.vec.step(self._actions)
-            self.launches += 1
-            self._results = {i: (obs[i].copy(), rew[i].copy(), bool(done[i]), None) for i in self._pending}
-            self._pending = {}
-            self._round += 1
-            self._cv.notify_all()
 
     def _submit(self, i, action):
         with self._cv:
-            if i not in self._active:
-                self._active.add(i)
-            my_round = self._round
-            self._pending[i] = action
-            self._maybe_launch()
-            while self._round == my_round:
+            self._pending[i] = np.asarray(action).astype(bool).reshape(-1)
+            while True:
+                if i in self._results:
+                    res = self._results.pop(i)
+                    if isinstance(res, BaseException):
+                        raise res
+                    return res
+                if not self._launching and i in self._pending:
+                    batch, self._pending = self._pending, {}
+                    self._launching = True
+                    break
                 self._cv.wait()
-            return self._results[i]
+        # leader: one masked launch for everything that was queued (the lock is released: others keep queueing)
+        out = None
+        try:
+            self._mask[:] = 0
+            for j, a in batch.items():
+                self._actions[j] = a
+                self._mask[j] = 1
+            obs, rew, done = self.vec.step_masked(self._actions, self._mask)
+            out = {j: (obs[j].copy(), rew[j].copy(), bool(done[j]), None) for j in batch}
+        except BaseException as ex:               # every caller of the failed batch gets the error, nobody hangs
+            out = {j: ex for j in batch}
+        with self._cv:
+            self._launching = False
+            self.launches += 1
+            self.stepped += len(batch)
+            self._results.update(out)
+            self._cv.notify_all()
+            mine = self._results.pop(i)
+        if isinstance(mine, BaseException):
+            raise mine
+        return mine

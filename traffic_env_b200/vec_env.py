@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (TE_ARRIVALS_INJECTED, TE_ARRIVALS_NONE, TE_ARRIVALS_PHILOX, TE_AUTO_RESET, TE_CAP, TE_DEVICE,
+from ._lib import (TE_CTRL_GIVEN, TE_CTRL_GREEDY, TE_ARRIVALS_INJECTED, TE_ARRIVALS_NONE, TE_ARRIVALS_PHILOX, TE_AUTO_RESET, TE_CAP, TE_DEVICE,
                    TE_HOST, TE_LEARN_SWITCH, TE_ORDERED_TRANSFERS, TE_REMI, TE_VALIDATE, check)
 
 ARCHETYPE = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], dtype=np.float32)  # traffic_env.py:35-43
@@ -107,7 +107,7 @@ class VecTrafficEnv(object):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.te_destroy(self._h)
             self._h = C.c_void_p()
-            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars", "_wire_buf"):
+            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars", "_wire_buf", "_multi"):
                 setattr(self, name, None)
             for ptr in self._pinned:
                 self._L.te_host_free(ptr)
@@ -174,6 +174,44 @@ class VecTrafficEnv(object):
         check(self._L.te_step(self._h, a.ctypes.data, k, self._obs.ctypes.data, self._reward.ctypes.data,
                               self._done.ctypes.data, TE_HOST, None))
         return self._obs, self._reward, self._done
+
+    def step_masked(self, actions, env_mask, k=None):
+        """step() for the envs whose mask entry is non-zero only (te_step_masked); the rows of the others in the returned
+        (reused) arrays keep what they held."""
+        a = self._actions(actions)
+        m = np.ascontiguousarray(np.asarray(env_mask).astype(bool), dtype=np.uint8)
+        k = self.ticks_per_step if k is None else int(k)
+        check(self._L.te_step_masked(self._h, a.ctypes.data, m.ctypes.data, k, self._obs.ctypes.data,
+                                     self._reward.ctypes.data, self._done.ctypes.data, TE_HOST, None))
+        return self._obs, self._reward, self._done
+
+    def step_multi(self, n_steps, actions=None, controller="greedy", k=None):
+        """n_steps actor steps in one launch under one controller decision (te_step_multi), host buffers: returns
+        (actions uint8[E, I], obs float[n_steps, E, 2r+I], reward float[n_steps, E, I], done uint8[n_steps, E]).
+        controller "greedy": the kernel evaluates algorithms/greedy.py:14-16 at launch; "given": `actions` holds."""
+        k = self.ticks_per_step if k is None else int(k)
+        n_steps = int(n_steps)
+        if getattr(self, "_multi_n", 0) < n_steps:
+            E, I = self.num_envs, self.intersections
+            self._multi = (self._host_array((n_steps, E, self.obs_len), np.float32),
+                           self._host_array((n_steps, E, I), np.float32), self._host_array((n_steps, E), np.uint8))
+            self._multi_n = n_steps
+        obs, rew, done = (x[:n_steps] for x in self._multi)
+        if controller == "greedy":
+            ctrl = TE_CTRL_GREEDY
+        else:
+            ctrl = TE_CTRL_GIVEN
+            self._actions(actions)
+        check(self._L.te_step_multi(self._h, n_steps, ctrl, self._act.ctypes.data, k, obs.ctypes.data, rew.ctypes.data,
+                                    done.ctypes.data, TE_HOST, None))
+        return self._act, obs, rew, done
+
+    def step_multi_device(self, n_steps, actions, obs, reward, done, controller="greedy", k=None, stream=None):
+        """te_step_multi on caller-owned device buffers ([n_steps, E, ...] outputs; `actions` [E, I] is written by the
+        greedy controller or read when controller == "given"); asynchronous."""
+        k = self.ticks_per_step if k is None else int(k)
+        check(self._L.te_step_multi(self._h, int(n_steps), TE_CTRL_GREEDY if controller == "greedy" else TE_CTRL_GIVEN,
+                                    _ptr(actions), k, _ptr(obs), _ptr(reward), _ptr(done), TE_DEVICE, stream))
 
     def step_wire(self, actions, k=None):
         """step() with the results left in the compact wire format (te_step_wire): a dict of views into one page-locked
