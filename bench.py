@@ -252,6 +252,9 @@ class Ctx(object):
 
 
 def setup_dist():
+    # helper threads of the host path (they expand wire records while the GPU works): what the host can spare per rank
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("TE_HOST_THREADS", str(max(2, min(8, (os.cpu_count() or 4) // max(world, 1) - 1))))
     import torch
     import torch.distributed as dist
     c = Ctx()
@@ -356,6 +359,30 @@ class Runner(object):
             s += k
         return acc
 
+    def host_steps_wire(self, n, s0=0):
+        """host_steps with the results left in the wire format (compact records, no float expansion on the host)."""
+        s, acc = s0, 0.0
+        while s < s0 + n:
+            if self.policy == "greedy" and self.multi:
+                k = min(SPACING - s % SPACING, s0 + n - s)
+                act, rec = self.env.step_multi_wire(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given")
+                if s % SPACING == 0:
+                    self.h_act[:] = act
+                for j in range(k):
+                    acc += float(rec["reward"][j, 0, 0]) + float(rec["passed"][j, 0, 0])
+            else:
+                k = 1
+                if self.policy == "greedy":
+                    if s % SPACING == 0:
+                        self.h_act[:] = self.env.greedy_actions()
+                    a = self.h_act
+                else:
+                    a = self.h_rand[s % 8]
+                rec = self.env.step_wire(a)
+                acc += float(rec["reward"][0, 0]) + float(rec["passed"][0, 0])
+            s += k
+        return acc
+
     def device_step(self, s):
         if self.policy == "greedy":
             if s % SPACING == 0:
@@ -405,13 +432,14 @@ class Runner(object):
         return dict(ms=ms_max, local=d, vu=tot[0], ticks=tot[1], asteps=tot[2], gen=tot[3], ovf=tot[4], episodes=tot[5],
                     launches=self.launches)
 
-    def timed_host(self, steps, warmup):
+    def timed_host(self, steps, warmup, wire=False):
         c, env = self.c, self.env
-        self.host_steps(warmup)
+        run = self.host_steps_wire if wire else self.host_steps
+        run(warmup)
         barrier(c)
         b0 = env.stats()["vehicle_updates"]
         t0 = time.perf_counter()
-        self.host_steps(steps)
+        run(steps)
         c.torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         vu = allreduce(c, [env.stats()["vehicle_updates"] - b0])[0]
@@ -560,10 +588,11 @@ def secondary_block(c, a, arith_peak):
     d = r3.timed_device(steps, warm)
     k_ms, k_vu = r3.kernel_times(min(steps, 8))
     e2e = r3.timed_host(max(3, steps // 2), 3)
+    e2e_wire = r3.timed_host(max(3, steps // 2), 3, wire=True)
     occ = r3.occupancy()
     out["grid3x3_L250_greedy"] = {
         "value": d["vu"] / (d["ms"] * 1e-3), "unit": "vehicle-updates/s", "envs_per_gpu": E3, "envs_total": E3 * c.world,
-        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "kernel_ms": k_ms,
+        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_wire": e2e_wire, "kernel_ms": k_ms,
         "env_actor_steps_per_sec": d["asteps"] / (d["ms"] * 1e-3),
         "roofline_compute": {"achieved": k_vu / (k_ms * 1e-3), "peak": arith_peak,
                              "frac": (k_vu / (k_ms * 1e-3) / arith_peak) if arith_peak else None},
@@ -575,11 +604,12 @@ def secondary_block(c, a, arith_peak):
         r4.device_steps(EPISODE_LEN + 17)     # past the first synchronous episode boundary
     d = r4.timed_device(steps, warm)
     e2e = r4.timed_host(max(3, steps // 2), 3)
+    e2e_wire = r4.timed_host(max(3, steps // 2), 3, wire=True)
     occ = r4.occupancy()
     st = r4.env.stats()
     out["config4_grid3x3_random_autoreset"] = {
         "value": d["vu"] / (d["ms"] * 1e-3), "unit": "vehicle-updates/s", "envs_per_gpu": E3, "envs_total": E3 * c.world,
-        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e,
+        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_wire": e2e_wire,
         "env_actor_steps_per_sec": d["asteps"] / (d["ms"] * 1e-3), "cars_per_env": occ["cars_per_env"],
         "episodes_closed_rank0": int(st["episodes"]),
         "mean_episode_return_rank0": (st["return_sum"] / st["episodes"]) if st["episodes"] else None,
@@ -666,12 +696,18 @@ def b200_arm(a):
     traffic, traffic_note = measured_traffic(a.workload)
 
     # end to end through the public API with HOST buffers: what the greedy agent does (greedy.py:13-17)
-    e2e = None
+    e2e = e2e_wire = None
     if not a.no_e2e:
+        e2e_wire = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
+        e2e_wire["api"] = ("VecTrafficEnv.step_multi_wire / step_wire: the same calls with the results left on the host as compact "
+                           "wire records (u8 passed / detected, f32 light / reward, u8 done), no float expansion")
         e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)))
-        e2e["api"] = ("VecTrafficEnv.step(actions) -> te_step(TE_HOST): actions H2D, obs/reward/done D2H into the env's "
-                      "page-locked host buffers every step (%s); VecTrafficEnv.greedy_actions() (device controller, "
-                      "actions D2H) every %d steps" % (env.host_path_note(), SPACING))
+        e2e["api"] = ("VecTrafficEnv.step_multi(n, controller='greedy') -> te_step_multi(TE_HOST): one call per greedy decision "
+                      "(%d actor steps); per actor step obs/reward/done of every env arrive in the env's page-locked host float "
+                      "arrays (%s, %s helper threads); the chosen actions come back too" %
+                      (SPACING, env.host_path_note(), os.environ.get("TE_HOST_THREADS")) if run.multi else
+                      "VecTrafficEnv.step(actions) -> te_step(TE_HOST) every step (%s); VecTrafficEnv.greedy_actions() every %d "
+                      "steps" % (env.host_path_note(), SPACING))
     clocks = sampler.stop(0, mark) if c.rank == 0 else None
 
     cpu = None
@@ -709,7 +745,7 @@ def b200_arm(a):
             "ordered_transfer_ticks_frac_rank0": loc["seq_fallback_ticks"] / max(loc["ticks"], 1),
             "steady_state_occupancy_rank0": occ,
             "target_8gpu": 1e11, "frac_of_per_gpu_target": value / c.world / 1.25e10,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
+            "clocks": clocks, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "kernel": "te_step_kernel", "kernel_ms": k_ms,
                          "actor_steps_per_launch": spl, "algorithmic_bytes_per_env_launch": bytes_env, "cars_per_env": cars_env,

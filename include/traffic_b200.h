@@ -167,6 +167,9 @@ typedef struct te_wire_layout_t {
 int te_wire_layout(const te_handle *h, te_wire_layout_t *out);
 int te_step_wire(te_handle *h, const uint8_t *actions, int32_t k_ticks, void *records, int memspace, void *stream);
 int te_expand_wire(const te_handle *h, const void *records, int32_t count, float *obs, float *reward, uint8_t *done);
+/* te_step_multi with wire records: records[n_steps][E][stride]. */
+int te_step_multi_wire(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks, void *records,
+                       int memspace, void *stream);
 
 /* One physics tick = bare TrafficEnv._step (traffic_env.py:224-248): obs int32[E, 2r+2I]
    (passed | detected | current_phase | elapsed), reward float[E, I], done uint8[E]. */

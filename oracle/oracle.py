@@ -182,7 +182,7 @@ class OracleEnv(object):
         self._L.to_philox_seed(self._h, int(seed), int(env_id),
                                self._gap_cdf.ctypes.data_as(C.POINTER(C.c_uint32)), int(self._gap_cdf.size))
 
-    def philox_arrivals(self, cap=64):
+    def philox_arrivals(self, cap=4096):
         buf = np.empty(cap, dtype=np.int32)
         n = self._L.to_philox_arrivals(self._h, buf.ctypes.data_as(C.POINTER(C.c_int)), cap)
         return buf[:n].copy()

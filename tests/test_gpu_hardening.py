@@ -316,3 +316,22 @@ def test_masked_step_touches_only_the_masked_envs():
         assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), e
         assert float(st["steps"][e]) == float(o.steps), e
     assert env.stats()["vehicle_updates"] == sum(o.vehicle_updates for o in oracles)
+
+
+def test_multi_step_wire_records():
+    """step_multi_wire == step_multi, field by field (records [n_steps, E, stride])."""
+    from traffic_env_b200 import VecTrafficEnv
+    E = 1000
+    kw = dict(m=3, n=3, length=250.0, num_envs=E, arrivals="philox", seed=4, local_cars_per_sec=0.5, ticks_per_step=10, remi=True)
+    a, b = VecTrafficEnv(**kw), VecTrafficEnv(**kw)
+    init = np.random.RandomState(1).randint(2, size=(E, 9))
+    a.reset(init_phase=init)
+    b.reset(init_phase=init)
+    for launch in range(8):
+        act_a, obs, rew, done = a.step_multi(3, controller="greedy")
+        act_b, rec = b.step_multi_wire(3, controller="greedy")
+        assert act_a.tobytes() == act_b.tobytes()
+        assert (rec["passed"].astype(np.float32) == obs[:, :, :36]).all() and (rec["detected"].astype(np.float32) == obs[:, :, 36:72]).all()
+        assert rec["light"].tobytes() == np.ascontiguousarray(obs[:, :, 72:]).tobytes()
+        assert rec["reward"].tobytes() == rew.tobytes() and (rec["done"] == done).all()
+    assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] > 0

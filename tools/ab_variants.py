@@ -40,7 +40,7 @@ def main():
             b.build(out=so_of(name), defines=defines)
         return
     args = sys.argv[2:]
-    workloads, steps, reps, names = ["grid10x10_L500_greedy", "grid3x3_L250_greedy"], 20, 2, []
+    workloads, steps, reps, names, extra = ["grid10x10_L500_greedy", "grid3x3_L250_greedy"], 21, 2, [], []
     while args:
         a = args.pop(0)
         if a == "--workloads":
@@ -49,6 +49,8 @@ def main():
             steps = int(args.pop(0))
         elif a == "--reps":
             reps = int(args.pop(0))
+        elif a.startswith("--bench-args"):
+            extra = (a.split("=", 1)[1] if "=" in a else args.pop(0)).split()
         else:
             names.append(a)
     res = {}
@@ -63,7 +65,7 @@ def main():
             for n in names:
                 env = env_of(n)
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", str(steps),
-                                    "--warmup", "5", "--no-e2e", "--no-cpu-baseline", "--no-secondary"], env=env,
+                                    "--warmup", "6", "--no-e2e", "--no-cpu-baseline", "--no-secondary"] + extra, env=env,
                                    capture_output=True, text=True)
                 try:
                     d = json.loads(r.stdout.strip().splitlines()[-1])

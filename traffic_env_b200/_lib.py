@@ -20,7 +20,7 @@ TE_CTRL_GIVEN, TE_CTRL_GREEDY = 0, 1
 
 EXPORTS = [
     "te_default_config", "te_device_count", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
-    "te_reset", "te_set_arrivals", "te_step", "te_step_masked", "te_step_multi", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
+    "te_reset", "te_set_arrivals", "te_step", "te_step_masked", "te_step_multi", "te_step_multi_wire", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
     "te_greedy_actions", "te_get_state", "te_set_state", "te_get_stats", "te_get_trip_times",
     "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_fdiv_const_exhaustive", "te_test_philox",
 ]
@@ -87,6 +87,7 @@ def load():
     L.te_step_wire.argtypes = [vp, vp, i32, vp, C.c_int, vp]
     L.te_step_masked.argtypes = [vp, vp, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_multi.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, C.c_int, vp]
+    L.te_step_multi_wire.argtypes = [vp, i32, i32, vp, i32, vp, C.c_int, vp]
     L.te_wire_layout.argtypes = [vp, C.POINTER(TeWireLayout)]
     L.te_expand_wire.argtypes = [vp, vp, i32, vp, vp, vp]
     L.te_remi_reward.argtypes = [vp, vp, C.c_int, vp]

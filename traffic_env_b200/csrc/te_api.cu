@@ -165,6 +165,9 @@ struct te_handle {
 // x 2 CTAs, 101.7 KB each; 3x3 grid: 64 threads x 16 CTAs).
 typedef void (*step_kernel_t)(const StepParams);
 struct StepVariant { step_kernel_t fn; int maxt; };
+#ifndef TE_MINB96
+#define TE_MINB96 10   // CTAs per SM the 96-thread variant is compiled for (10: 64 registers; 9: 72)
+#endif
 #ifndef TE_FAST_ARCH
 #define TE_FAST_ARCH 1   // compile the car loop a second time for the reference's archetype (IdmConst.pow2 && delta_is_four)
 #endif
@@ -185,7 +188,7 @@ static StepVariant step_variant_for(int threads, bool validate, bool fa, bool gr
   }
   if (grouped) {
     if (threads <= 64) return pick_fa<64, 16, false, true>(fa);
-    if (threads <= 96) return pick_fa<96, 10, false, true>(fa);   // default 3x3 grid: two envs (2 x 48 roads) on three warps, 20 envs per SM
+    if (threads <= 96) return pick_fa<96, TE_MINB96, false, true>(fa);   // default 3x3 grid: two envs (2 x 48 roads) on three warps, 20 envs per SM
     if (threads <= 128) return pick_fa<128, 8, false, true>(fa);
     if (threads <= 160) return pick_fa<160, 6, false, true>(fa);
     if (threads <= 192) return pick_fa<192, 5, false, true>(fa);
@@ -765,6 +768,14 @@ extern "C" int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, 
   if (controller != TE_CTRL_GIVEN && controller != TE_CTRL_GREEDY) return fail("te_step_multi: unknown controller %d", controller);
   StepReq q; q.actions = actions; q.K = k_ticks; q.nsteps = n_steps; q.controller = controller == TE_CTRL_GREEDY ? CTRL_GREEDY : CTRL_GIVEN;
   q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace; q.stream = stream; q.who = "te_step_multi";
+  return launch_step(h, q);
+}
+
+extern "C" int te_step_multi_wire(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks,
+                                  void *records, int memspace, void *stream) {
+  if (controller != TE_CTRL_GIVEN && controller != TE_CTRL_GREEDY) return fail("te_step_multi_wire: unknown controller %d", controller);
+  StepReq q; q.actions = actions; q.K = k_ticks; q.nsteps = n_steps; q.controller = controller == TE_CTRL_GREEDY ? CTRL_GREEDY : CTRL_GIVEN;
+  q.obs = records; q.memspace = memspace; q.stream = stream; q.wire_only = true; q.who = "te_step_multi_wire";
   return launch_step(h, q);
 }
 

@@ -310,6 +310,9 @@ __device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int 
 }
 
 constexpr int NO_OVERFLOW = 0x7fffffff;
+#ifndef TE_UNIFORM_CAR_LOOP
+#define TE_UNIFORM_CAR_LOOP 1   // measured: the per-lane trip count (0) is 4.5 % / 8 % slower (10x10 / 3x3): lanes drifting apart cost more than the re-convergence
+#endif
 
 // GROUPED = false: one env per CTA (p.G == 1), everything about env groups folds away at compile time.
 template <int MAXT, int MINB, bool VALIDATE, bool FA, bool GROUPED>
@@ -426,13 +429,20 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       }
     }
   }
+  // phase / elapsed update of the first tick (traffic_env.py:225-232); later ticks of the launch repeat the same
+  // action and are derived in closed form below.  A CTA has fewer intersections than threads: thread i < nI handles
+  // intersection i.  Its global loads are issued before the wait on the bulk copy, so the two latencies overlap.
+  int li_ph = 0, li_el = 0, li_act = 0, li_pd = 0;
+  if (tid < nI) {
+    li_ph = p.phase[ibase + tid] != 0;
+    li_el = p.elapsed[ibase + tid];
+    li_pd = p.passed_dst[ibase + tid];
+    if (p.controller != CTRL_GREEDY) li_act = p.actions[ibase + tid] != 0;
+  }
   __syncthreads();       // (the mbarrier is initialised for everybody)
   mbar_wait(s.mbar, 0);  // the ring planes have landed
-  for (int i = tid; i < nI; i += blockDim.x) {
-    // phase / elapsed update of the first tick (traffic_env.py:225-232); later ticks of the launch
-    // repeat the same action and are derived in closed form below.
-    int ph = p.phase[ibase + i] != 0;
-    int act;
+  if (tid < nI) {
+    const int i = tid;
     if (p.controller == CTRL_GREEDY) {
       // algorithms/greedy.py:14-16: cars_on_roads()[row, col, :] . [1, 1, -1, -1] < 0 from the ring indices as staged
       const int g = i / p.I, ii = i - g * p.I;
@@ -442,17 +452,14 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
         const int cn = ring_count(w0 & 0xff, (w0 >> 8) & 0xff);
         bal += dd < 2 ? cn : -cn;
       }
-      act = bal < 0;
-      if (p.actions_out) p.actions_out[ibase + i] = (uint8_t)act;
-    } else {
-      act = p.actions[ibase + i] != 0;
+      li_act = bal < 0;
+      if (p.actions_out) p.actions_out[ibase + i] = (uint8_t)li_act;
     }
-    int el = p.elapsed[ibase + i];
     int change;
-    if (learn_switch) { change = act; ph ^= act; } else { change = ph ^ act; ph = act; }
-    el = (el + 1) * (change ? 0 : 1);
-    s.phase[i] = (uint8_t)ph; s.act[i] = (uint8_t)act; s.elapsed[i] = el;
-    s.pdst[i] = p.passed_dst[ibase + i]; s.ovf[i] = 0;
+    if (learn_switch) { change = li_act; li_ph ^= li_act; } else { change = li_ph ^ li_act; li_ph = li_act; }
+    li_el = (li_el + 1) * (change ? 0 : 1);
+    s.phase[i] = (uint8_t)li_ph; s.act[i] = (uint8_t)li_act; s.elapsed[i] = li_el;
+    s.pdst[i] = (uint8_t)li_pd; s.ovf[i] = 0;
   }
   if (tid >= nrows) {    // a padding row: an empty ring behind a free road, like te_reset leaves one
     s.xs[tid * CAP] = __uint_as_float(pack_meta(1, 1, 0)); s.vs[tid * CAP] = __int_as_float(0);
@@ -610,8 +617,15 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       }
       __syncwarp();  // every run has read the leader of its first car before any lane overwrites a slot
       unsigned int acc = 0u;
+#if TE_UNIFORM_CAR_LOOP
       for (int i = 0; i < q; i++) {
         if (i < cnt) {
+#else
+      // per-lane trip count: the lanes of the last, shorter runs simply leave the loop early (nothing inside is a
+      // warp-level operation), which spares the loop a uniform counter and a warp re-convergence per iteration
+      for (int i = cnt; i > 0; i--) {
+        {
+#endif
           float xn = lds_f32(addr), vn = lds_f32_off<VOFF>(addr);
           const float xl = px, vl = pv, ll = pl;
           px = xn; pv = vn; pl = c.len;

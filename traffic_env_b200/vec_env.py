@@ -107,7 +107,7 @@ class VecTrafficEnv(object):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.te_destroy(self._h)
             self._h = C.c_void_p()
-            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars", "_wire_buf", "_multi"):
+            for name in ("_obs", "_obs_raw", "_reward", "_done", "_act", "_cars", "_wire_buf", "_multi", "_multi_wire"):
                 setattr(self, name, None)
             for ptr in self._pinned:
                 self._L.te_host_free(ptr)
@@ -206,6 +206,27 @@ class VecTrafficEnv(object):
                                     done.ctypes.data, TE_HOST, None))
         return self._act, obs, rew, done
 
+    def _wire_views(self, w):
+        """dict of views into a record buffer [..., E, stride]."""
+        r, I, wl = self.train_roads, self.intersections, self.wire
+        return {"passed": w[..., wl.passed:wl.passed + r], "detected": w[..., wl.detected:wl.detected + r],
+                "light": w[..., wl.light:wl.light + 4 * I].view(np.float32),
+                "reward": w[..., wl.reward:wl.reward + 4 * I].view(np.float32), "done": w[..., wl.done]}
+
+    def step_multi_wire(self, n_steps, actions=None, controller="greedy", k=None):
+        """step_multi with the results left as wire records: (actions, dict of views [n_steps, E, ...])."""
+        k = self.ticks_per_step if k is None else int(k)
+        n_steps = int(n_steps)
+        if getattr(self, "_multi_wire_n", 0) < n_steps:
+            self._multi_wire = self._host_array((n_steps, self.num_envs, self.wire.stride), np.uint8)
+            self._multi_wire_n = n_steps
+        buf = self._multi_wire[:n_steps]
+        if controller != "greedy":
+            self._actions(actions)
+        check(self._L.te_step_multi_wire(self._h, n_steps, TE_CTRL_GREEDY if controller == "greedy" else TE_CTRL_GIVEN,
+                                         self._act.ctypes.data, k, buf.ctypes.data, TE_HOST, None))
+        return self._act, self._wire_views(buf)
+
     def step_multi_device(self, n_steps, actions, obs, reward, done, controller="greedy", k=None, stream=None):
         """te_step_multi on caller-owned device buffers ([n_steps, E, ...] outputs; `actions` [E, I] is written by the
         greedy controller or read when controller == "given"); asynchronous."""
@@ -223,10 +244,7 @@ class VecTrafficEnv(object):
         if self._wire_buf is None:
             self._wire_buf = self._host_array((E, wl.stride), np.uint8)
         check(self._L.te_step_wire(self._h, a.ctypes.data, k, self._wire_buf.ctypes.data, TE_HOST, None))
-        w = self._wire_buf
-        return {"passed": w[:, wl.passed:wl.passed + r], "detected": w[:, wl.detected:wl.detected + r],
-                "light": w[:, wl.light:wl.light + 4 * I].view(np.float32),
-                "reward": w[:, wl.reward:wl.reward + 4 * I].view(np.float32), "done": w[:, wl.done]}
+        return self._wire_views(self._wire_buf)
 
     def expand_wire(self, env_begin=0, count=None):
         """Float (obs, reward, done) of step() from the records of the last step_wire()."""
