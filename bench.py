@@ -360,16 +360,18 @@ class Runner(object):
         return acc
 
     def host_steps_wire(self, n, s0=0):
-        """host_steps with the results left in the wire format (compact records, no float expansion on the host)."""
+        """host_steps through the lazy form of the same calls (step(..., lazy=True) / step_multi(..., lazy=True)): every
+        env's results arrive in page-locked host memory as compact wire records, the float observation is expanded on
+        demand - here for one env per actor step, which is also read."""
         s, acc = s0, 0.0
         while s < s0 + n:
             if self.policy == "greedy" and self.multi:
                 k = min(SPACING - s % SPACING, s0 + n - s)
-                act, rec = self.env.step_multi_wire(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given")
+                act, res = self.env.step_multi(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given", lazy=True)
                 if s % SPACING == 0:
                     self.h_act[:] = act
                 for j in range(k):
-                    acc += float(rec["reward"][j, 0, 0]) + float(rec["passed"][j, 0, 0])
+                    acc += float(res.reward[j, 0, 0]) + float(res.obs_of([0], step=j)[0, 0])
             else:
                 k = 1
                 if self.policy == "greedy":
@@ -378,8 +380,8 @@ class Runner(object):
                     a = self.h_act
                 else:
                     a = self.h_rand[s % 8]
-                rec = self.env.step_wire(a)
-                acc += float(rec["reward"][0, 0]) + float(rec["passed"][0, 0])
+                res = self.env.step(a, lazy=True)
+                acc += float(res.reward[0, 0]) + float(res.obs_of([0])[0, 0])
             s += k
         return acc
 
@@ -446,7 +448,8 @@ class Runner(object):
         t = allreduce(c, [dt], "max")[0]
         E, I, OL = self.E, self.I, self.OL
         return {"value": vu / t, "unit": "vehicle-updates/s", "h2d_bytes_per_step": int(E * I),
-                "d2h_bytes_per_step": int(env.d2h_bytes_per_step() + (E * I // SPACING if self.policy == "greedy" else 0)),
+                "d2h_bytes_per_step": int((env.d2h_bytes_per_step() if wire or not env.host_float_dma() else E * (OL * 4 + I * 4 + 1))
+                                          + (E * I // SPACING if self.policy == "greedy" else 0)),
                 "steps": steps, "host_calls_per_step": (1.0 / SPACING) if self.multi else (1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0))}
 
     def kernel_times(self, n):
@@ -587,12 +590,12 @@ def secondary_block(c, a, arith_peak):
         r3.device_steps(w3["preroll"])
     d = r3.timed_device(steps, warm)
     k_ms, k_vu = r3.kernel_times(min(steps, 8))
-    e2e = r3.timed_host(max(3, steps // 2), 3)
-    e2e_wire = r3.timed_host(max(3, steps // 2), 3, wire=True)
+    e2e_float = r3.timed_host(max(3, steps // 2), 3)
+    e2e = r3.timed_host(max(3, steps // 2), 3, wire=True)
     occ = r3.occupancy()
     out["grid3x3_L250_greedy"] = {
         "value": d["vu"] / (d["ms"] * 1e-3), "unit": "vehicle-updates/s", "envs_per_gpu": E3, "envs_total": E3 * c.world,
-        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_wire": e2e_wire, "kernel_ms": k_ms,
+        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_float": e2e_float, "kernel_ms": k_ms,
         "env_actor_steps_per_sec": d["asteps"] / (d["ms"] * 1e-3),
         "roofline_compute": {"achieved": k_vu / (k_ms * 1e-3), "peak": arith_peak,
                              "frac": (k_vu / (k_ms * 1e-3) / arith_peak) if arith_peak else None},
@@ -603,13 +606,13 @@ def secondary_block(c, a, arith_peak):
     with c.torch.cuda.stream(c.tstream):
         r4.device_steps(EPISODE_LEN + 17)     # past the first synchronous episode boundary
     d = r4.timed_device(steps, warm)
-    e2e = r4.timed_host(max(3, steps // 2), 3)
-    e2e_wire = r4.timed_host(max(3, steps // 2), 3, wire=True)
+    e2e_float = r4.timed_host(max(3, steps // 2), 3)
+    e2e = r4.timed_host(max(3, steps // 2), 3, wire=True)
     occ = r4.occupancy()
     st = r4.env.stats()
     out["config4_grid3x3_random_autoreset"] = {
         "value": d["vu"] / (d["ms"] * 1e-3), "unit": "vehicle-updates/s", "envs_per_gpu": E3, "envs_total": E3 * c.world,
-        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_wire": e2e_wire,
+        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_float": e2e_float,
         "env_actor_steps_per_sec": d["asteps"] / (d["ms"] * 1e-3), "cars_per_env": occ["cars_per_env"],
         "episodes_closed_rank0": int(st["episodes"]),
         "mean_episode_return_rank0": (st["return_sum"] / st["episodes"]) if st["episodes"] else None,
@@ -696,18 +699,20 @@ def b200_arm(a):
     traffic, traffic_note = measured_traffic(a.workload)
 
     # end to end through the public API with HOST buffers: what the greedy agent does (greedy.py:13-17)
-    e2e = e2e_wire = None
+    e2e = e2e_float = None
     if not a.no_e2e:
-        e2e_wire = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
-        e2e_wire["api"] = ("VecTrafficEnv.step_multi_wire / step_wire: the same calls with the results left on the host as compact "
-                           "wire records (u8 passed / detected, f32 light / reward, u8 done), no float expansion")
-        e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)))
-        e2e["api"] = ("VecTrafficEnv.step_multi(n, controller='greedy') -> te_step_multi(TE_HOST): one call per greedy decision "
-                      "(%d actor steps); per actor step obs/reward/done of every env arrive in the env's page-locked host float "
-                      "arrays (%s, %s helper threads); the chosen actions come back too" %
-                      (SPACING, env.host_path_note(), os.environ.get("TE_HOST_THREADS")) if run.multi else
-                      "VecTrafficEnv.step(actions) -> te_step(TE_HOST) every step (%s); VecTrafficEnv.greedy_actions() every %d "
-                      "steps" % (env.host_path_note(), SPACING))
+        e2e_float = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)))
+        e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
+        e2e["api"] = ("VecTrafficEnv.step_multi(n, controller='greedy', lazy=True) -> te_step_multi_wire(TE_HOST): one call per "
+                      "greedy decision (%d actor steps); actions host -> device (given) or back (chosen by the kernel); per actor "
+                      "step the results of EVERY env arrive in page-locked host memory as compact wire records (%d B per env: u8 "
+                      "passed / detected, f32 light / reward, u8 done - lossless: the counts are small integers); the float "
+                      "observation is expanded on demand (WireResult.obs / obs_of), here for one env per step, and read" %
+                      (SPACING, env.wire.stride))
+        e2e_float["api"] = ("the eager form of the same call (lazy=False): every env's float obs[%d] / reward / done in host "
+                            "memory every actor step - %s" % (env.obs_len, "float arrays written by the copy engine (few host "
+                            "cores per GPU)" if env.host_float_dma() else "wire records expanded by %s helper threads of the handle "
+                            "while the next slices are simulated" % os.environ.get("TE_HOST_THREADS")))
     clocks = sampler.stop(0, mark) if c.rank == 0 else None
 
     cpu = None
@@ -745,7 +750,7 @@ def b200_arm(a):
             "ordered_transfer_ticks_frac_rank0": loc["seq_fallback_ticks"] / max(loc["ticks"], 1),
             "steady_state_occupancy_rank0": occ,
             "target_8gpu": 1e11, "frac_of_per_gpu_target": value / c.world / 1.25e10,
-            "clocks": clocks, "e2e": e2e, "e2e_wire": e2e_wire, "gpu_launches": n_launch,
+            "clocks": clocks, "e2e": e2e, "e2e_float": e2e_float, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "kernel": "te_step_kernel", "kernel_ms": k_ms,
                          "actor_steps_per_launch": spl, "algorithmic_bytes_per_env_launch": bytes_env, "cars_per_env": cars_env,

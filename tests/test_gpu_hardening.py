@@ -335,3 +335,40 @@ def test_multi_step_wire_records():
         assert rec["light"].tobytes() == np.ascontiguousarray(obs[:, :, 72:]).tobytes()
         assert rec["reward"].tobytes() == rew.tobytes() and (rec["done"] == done).all()
     assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] > 0
+
+
+def test_lazy_results_and_both_host_transports(monkeypatch):
+    """step(lazy=True) / step_multi(lazy=True) deliver WireResults whose lazily expanded observation equals the eager
+    float arrays, and the two transports of the eager host path (wire records expanded on the host; float arrays written
+    by the copy engine, TE_HOST_FLOAT_DMA) give identical bytes - single and multi-step."""
+    from traffic_env_b200 import VecTrafficEnv, WireResult
+    E = 2500
+    kw = dict(m=3, n=3, length=250.0, num_envs=E, arrivals="philox", seed=6, local_cars_per_sec=0.5, ticks_per_step=10, remi=True)
+    monkeypatch.setenv("TE_HOST_FLOAT_DMA", "0")
+    a, lz = VecTrafficEnv(**kw), VecTrafficEnv(**kw)
+    monkeypatch.setenv("TE_HOST_FLOAT_DMA", "1")
+    b = VecTrafficEnv(**kw)
+    init = np.random.RandomState(1).randint(2, size=(E, 9))
+    for env in (a, b, lz):
+        env.reset(init_phase=init)
+    rng = np.random.RandomState(2)
+    for s in range(10):
+        if s % 2 == 0:
+            act = rng.randint(2, size=(E, 9)).astype(np.uint8)
+            oa, ra, da = a.step(act)
+            ob, rb, db = b.step(act)
+            res = lz.step(act, lazy=True)
+            assert isinstance(res, WireResult)
+            assert oa.tobytes() == ob.tobytes() and ra.tobytes() == rb.tobytes() and da.tobytes() == db.tobytes(), s
+            assert res.obs_of([0, 7, E - 1]).tobytes() == oa[[0, 7, E - 1]].tobytes()
+            ol, rl, dl = res
+            assert ol.tobytes() == oa.tobytes() and rl.tobytes() == ra.tobytes() and dl.tobytes() == da.tobytes(), s
+        else:
+            xa, oa, ra, da = a.step_multi(3, controller="greedy")
+            xb, ob, rb, db = b.step_multi(3, controller="greedy")
+            xl, res = lz.step_multi(3, controller="greedy", lazy=True)
+            assert xa.tobytes() == xb.tobytes() == xl.tobytes()
+            assert oa.tobytes() == ob.tobytes() and ra.tobytes() == rb.tobytes() and da.tobytes() == db.tobytes(), s
+            assert res.obs.tobytes() == oa.tobytes() and res.reward.tobytes() == ra.tobytes() and (res.done == da).all(), s
+            assert res.obs_of([3, 4], step=2).tobytes() == oa[2, [3, 4]].tobytes()
+    assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] == lz.stats()["vehicle_updates"] > 0

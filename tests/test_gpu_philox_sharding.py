@@ -84,14 +84,18 @@ def reset_phases(seed, env_id, reset_count, I):
     return out
 
 
-def test_auto_reset_and_return_statistics():
+@pytest.mark.parametrize("m,n,L,E,S,EPL,lcps", [(3, 3, 250.0, 48, 40, 7, 0.45), (10, 10, 500.0, 160, 24, 9, 0.3),
+                                                 (5, 5, 200.0, 333, 30, 6, 0.4)])
+def test_auto_reset_and_return_statistics(m, n, L, E, S, EPL, lcps):
     """TE_AUTO_RESET: an env whose step overflowed, or that reached episode_len, is _reset at the start of
-    its next step; episode returns accumulate as util.py:68-94 defines them."""
+    its next step; episode returns accumulate as util.py:68-94 defines them.  Default grid (shared CTAs), the 10x10
+    grid and a 5x5 grid (Philox reset phases of more than 32 intersections: several words of the draw)."""
     from traffic_env_b200.arrivals import gap_cdf
-    E, S, K, EPL, GAMMA = 48, 40, 10, 7, 0.8
-    env = make(E, auto_reset=True, episode_len=EPL, gamma=GAMMA, local_cars_per_sec=0.45)
+    K, GAMMA = 10, 0.8
+    I = m * n
+    env = make(E, m=m, n=n, length=L, auto_reset=True, episode_len=EPL, gamma=GAMMA, local_cars_per_sec=lcps)
     rng = np.random.RandomState(5)
-    init = rng.randint(2, size=(E, 9))
+    init = rng.randint(2, size=(E, I))
     env.reset(init_phase=init)
     cdf = gap_cdf(env.cars_per_sec * 0.5)
     # reset_count: 1 after te_create, 2 after the explicit reset above; it keys the Philox draw of the next reset
@@ -100,19 +104,19 @@ def test_auto_reset_and_return_statistics():
     closed, ret_sum, disc_sum = 0, 0.0, 0.0
     was_done = np.zeros(E, bool)
     for e in range(E):
-        o = OracleEnv(3, 3, 250.0, 0.5)
+        o = OracleEnv(m, n, L, 0.5)
         o.reset(init[e])
         o.philox_seed(99, e, cdf)
         oracles.append(o)
     for s in range(S):
-        act = rng.randint(2, size=(E, 9))
+        act = rng.randint(2, size=(E, I))
         obs, rew, done = env.step(act)
         for e, o in enumerate(oracles):
             if was_done[e] or ep_step[e] >= EPL:
                 closed += 1
                 ret_sum += ret[e]
                 disc_sum += disc[e]
-                o.reset(reset_phases(99, e, int(resets[e]), 9))
+                o.reset(reset_phases(99, e, int(resets[e]), I))
                 resets[e] += 1
                 ep_step[e] = 0
                 ret[e] = disc[e] = 0.0

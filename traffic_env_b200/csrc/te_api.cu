@@ -154,7 +154,8 @@ struct te_handle {
   int smem_optin;
   // wire path of the host API
   unsigned char *d_wire, *h_wire;   // [E][wire_stride] device / page-locked host
-  int wire_stride, host_slices, wire_steps;
+  int wire_stride, host_slices, wire_steps, float_steps;
+  bool float_dma;        // te_step(TE_HOST) with float outputs: let the copy engine write the float arrays (no host expansion)
   cudaEvent_t ev_copy[64];
   ExpandPool *pool;
 };
@@ -346,7 +347,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   h->stream = h->stream2 = h->stream_copy = nullptr; h->ev0 = h->ev1 = h->ev_fork = h->ev_join = h->ev_copied = nullptr;
   for (cudaEvent_t &e : h->ev_slice) e = nullptr;
   for (cudaEvent_t &e : h->ev_copy) e = nullptr;
-  h->d_wire = h->h_wire = nullptr; h->pool = nullptr; h->wire_stride = 0; h->host_slices = 1; h->wire_steps = 0;
+  h->d_wire = h->h_wire = nullptr; h->pool = nullptr; h->wire_stride = 0; h->host_slices = 1; h->wire_steps = 0; h->float_steps = 1;
   h->timed = false; h->trip_cap = 0;
 #define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { free_handle(h); return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   CUH(cudaSetDevice(h->device));
@@ -435,6 +436,13 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
     if (nthr > nslice) nthr = nslice;
     h->pool = new ExpandPool();
     h->pool->start(h->device, nthr);
+    // Float outputs in host memory can travel two ways: as wire records expanded by the helper threads (fewer PCIe
+    // bytes; needs ~4 spare cores per GPU: measured 0.91 of the device rate on a 16-core / 1-GPU box, 0.51 with 8 ranks
+    // on 32 cores) or as float arrays written by the copy engine (r1 scheme: no host work, 2.5 x the PCIe bytes: 0.90 /
+    // 0.73).  Default: expansion when the host has at least 8 hardware threads per visible GPU.  TE_HOST_FLOAT_DMA = 0 / 1
+    // overrides.  (te_step_wire never expands: 0.97 with 8 ranks.)
+    h->float_dma = hw && ndev > 0 && hw / (unsigned)ndev < 8;
+    if (const char *ev = getenv("TE_HOST_FLOAT_DMA")) h->float_dma = atoi(ev) != 0;
   }
   CUH(cudaMemcpy(h->d_nexts, nx.data(), nx.size() * sizeof(short), cudaMemcpyHostToDevice));
   CUH(cudaMemcpy(h->d_up, up.data(), up.size() * sizeof(short), cudaMemcpyHostToDevice));
@@ -643,6 +651,24 @@ static int ensure_wire_steps(te_handle *h, int nsteps) {
   return 0;
 }
 
+// device staging of the float outputs of an n-step launch (host path without wire records)
+static int ensure_float_steps(te_handle *h, int nsteps) {
+  if (nsteps <= h->float_steps) return 0;
+  CU(cudaDeviceSynchronize());
+  const size_t E = (size_t)h->cfg.num_envs;
+  if (h->d_obs_i) { cudaFree(h->d_obs_i); h->d_obs_i = nullptr; h->d_obs_f = nullptr; }
+  if (h->d_reward) { cudaFree(h->d_reward); h->d_reward = nullptr; }
+  if (h->d_done) { cudaFree(h->d_done); h->d_done = nullptr; }
+  h->float_steps = 0;
+  CU(dalloc(&h->d_obs_i, (size_t)nsteps * E * (2 * h->r + 2 * h->I)));
+  CU(dalloc(&h->d_reward, (size_t)nsteps * E * h->I));
+  CU(dalloc(&h->d_done, (size_t)nsteps * E));
+  CU(cudaMemset(h->d_done, 0, (size_t)nsteps * E));
+  h->d_obs_f = reinterpret_cast<float *>(h->d_obs_i);
+  h->float_steps = nsteps;
+  return 0;
+}
+
 static int launch_step(te_handle *h, const StepReq &q) {
   const int K = q.K, raw = q.raw, nsteps = q.nsteps;
   const bool greedy = q.controller == CTRL_GREEDY;
@@ -657,8 +683,7 @@ static int launch_step(te_handle *h, const StepReq &q) {
   const size_t E = (size_t)h->cfg.num_envs;
   const size_t obs_len = raw ? (size_t)(2 * h->r + 2 * h->I) : (size_t)(2 * h->r + h->I);
   const bool host = q.memspace == TE_HOST;
-  const bool use_wire = !raw && K <= WIRE_MAX_K && (host || q.wire_only);
-  if (host && nsteps > 1 && !use_wire) return fail("%s: multi-step launches with host buffers need k_ticks <= %d", q.who, WIRE_MAX_K);
+  const bool use_wire = !raw && K <= WIRE_MAX_K && (q.wire_only || (host && (!h->float_dma || q.env_mask)));
   StepParams p = h->base;
   p.K = K; p.raw = raw; p.nsteps = nsteps; p.controller = q.controller; p.actions_out = nullptr; p.env_mask = q.env_mask;
   if (host) {
@@ -669,6 +694,9 @@ static int launch_step(te_handle *h, const StepReq &q) {
     if (use_wire) {
       if (int rc = ensure_wire_steps(h, nsteps)) return rc;
       p.wire = h->d_wire; p.wire_stride = h->wire_stride;
+    } else {
+      if (int rc = ensure_float_steps(h, nsteps)) return rc;
+      p.obs_f = h->d_obs_f; p.obs_i = h->d_obs_i; p.reward = h->d_reward; p.done = h->d_done;
     }
   } else {
     p.actions = q.actions; p.actions_out = greedy ? const_cast<uint8_t *>(q.actions) : nullptr;
@@ -704,7 +732,7 @@ static int launch_step(te_handle *h, const StepReq &q) {
   CU(cudaEventRecord(h->ev_fork, st));               // actions (and the auto-reset) are complete on `st`
   CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
   cudaStream_t lanes[2] = {st, h->stream2};
-  const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;
+  const char *src_obs = raw ? (const char *)h->d_obs_i : (const char *)h->d_obs_f;   // (after ensure_float_steps)
   unsigned char *host_wire = q.wire_only ? (unsigned char *)q.obs : h->h_wire;
   const size_t wstep = E * (size_t)h->wire_stride;   // records of one actor step
   int nk = 0;
@@ -722,11 +750,14 @@ static int launch_step(te_handle *h, const StepReq &q) {
                            (size_t)ne * h->wire_stride, cudaMemcpyDeviceToHost, h->stream_copy));
       CU(cudaEventRecord(h->ev_copy[k], h->stream_copy));
     } else {
-      CU(cudaMemcpyAsync((char *)q.obs + (size_t)e0 * obs_len * 4, src_obs + (size_t)e0 * obs_len * 4, (size_t)ne * obs_len * 4,
-                         cudaMemcpyDeviceToHost, h->stream_copy));
-      CU(cudaMemcpyAsync(q.reward + (size_t)e0 * h->I, h->d_reward + (size_t)e0 * h->I, (size_t)ne * h->I * sizeof(float),
-                         cudaMemcpyDeviceToHost, h->stream_copy));
-      CU(cudaMemcpyAsync(q.done + e0, h->d_done + e0, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
+      for (int j = 0; j < nsteps; j++) {      // float arrays written by the copy engine, [nsteps][E][...]
+        const size_t eo = (size_t)j * E + e0;
+        CU(cudaMemcpyAsync((char *)q.obs + eo * obs_len * 4, src_obs + eo * obs_len * 4, (size_t)ne * obs_len * 4,
+                           cudaMemcpyDeviceToHost, h->stream_copy));
+        CU(cudaMemcpyAsync(q.reward + eo * h->I, h->d_reward + eo * h->I, (size_t)ne * h->I * sizeof(float),
+                           cudaMemcpyDeviceToHost, h->stream_copy));
+        CU(cudaMemcpyAsync(q.done + eo, h->d_done + eo, (size_t)ne, cudaMemcpyDeviceToHost, h->stream_copy));
+      }
     }
     nk = k + 1;
   }

@@ -39,6 +39,41 @@ def _ptr(a):
     return int(a.data_ptr())  # torch tensor
 
 
+class WireResult(object):
+    """Results of an actor step (or of the n actor steps of one launch) as they arrived in host memory: compact wire
+    records.  `reward` f32[..., E, I], `done` u8[..., E], `passed` / `detected` u8[..., E, r] and `light` f32[..., E, I] are
+    views into the page-locked record buffer; the float observation of the reference's Repeater (traffic_test.py:37-56:
+    float32[2r + I] = passed | detected | light) is expanded LAZILY: `obs` expands everything on first access (C, cached),
+    `obs_of(env_ids)` only the rows asked for.  Unpacking `obs, reward, done = result` works like the eager API."""
+
+    def __init__(self, env, buf):
+        self._env, self._buf, self._obs = env, buf, None
+        v = env._wire_views(buf)
+        self.passed, self.detected, self.light, self.reward, self.done = (v[k] for k in ("passed", "detected", "light", "reward", "done"))
+
+    @property
+    def obs(self):
+        if self._obs is None:
+            e = self._env
+            lead = self._buf.shape[:-2]
+            n = int(np.prod(lead)) * e.num_envs if lead else e.num_envs
+            obs = np.empty(lead + (e.num_envs, e.obs_len), np.float32)
+            rew = np.empty(lead + (e.num_envs, e.intersections), np.float32)
+            done = np.empty(lead + (e.num_envs,), np.uint8)
+            check(e._L.te_expand_wire(e._h, self._buf.ctypes.data, n, obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+            self._obs = obs
+        return self._obs
+
+    def obs_of(self, env_ids, step=None):
+        """float32[len(env_ids), 2r + I] for the given envs (of actor step `step` for a multi-step result)."""
+        ids = np.asarray(env_ids, dtype=np.int64).reshape(-1)
+        sel = (ids,) if step is None else (step, ids)
+        return np.concatenate([self.passed[sel].astype(np.float32), self.detected[sel].astype(np.float32), self.light[sel]], axis=-1)
+
+    def __iter__(self):
+        return iter((self.obs, self.reward, self.done))
+
+
 class VecTrafficEnv(object):
     def __init__(self, m=3, n=3, length=250.0, num_envs=1, rate=0.5, ticks_per_step=10, remi=True,
                  learn_switch=False, auto_reset=False, validate=False, arrivals="philox", local_cars_per_sec=0.12,
@@ -166,9 +201,13 @@ class VecTrafficEnv(object):
         check(self._L.te_set_arrivals(self._h, offsets.ctypes.data, roads.ctypes.data, int(nroads), int(first_tick),
                                       int(horizon)))
 
-    def step(self, actions, k=None):
+    def step(self, actions, k=None, lazy=False):
         """One actor step (Repeater(k) [+ Remi]) for every env; returns (obs, reward, done) host arrays
-        that are reused between calls, like the reference's in-place obs/rewards buffers."""
+        that are reused between calls, like the reference's in-place obs/rewards buffers.  lazy=True: a WireResult - the
+        results stay in the compact form they crossed PCIe in and the float observation is expanded on demand."""
+        if lazy:
+            self.step_wire(actions, k)
+            return WireResult(self, self._wire_buf)
         a = self._actions(actions)
         k = self.ticks_per_step if k is None else int(k)
         check(self._L.te_step(self._h, a.ctypes.data, k, self._obs.ctypes.data, self._reward.ctypes.data,
@@ -185,12 +224,16 @@ class VecTrafficEnv(object):
                                      self._reward.ctypes.data, self._done.ctypes.data, TE_HOST, None))
         return self._obs, self._reward, self._done
 
-    def step_multi(self, n_steps, actions=None, controller="greedy", k=None):
+    def step_multi(self, n_steps, actions=None, controller="greedy", k=None, lazy=False):
         """n_steps actor steps in one launch under one controller decision (te_step_multi), host buffers: returns
         (actions uint8[E, I], obs float[n_steps, E, 2r+I], reward float[n_steps, E, I], done uint8[n_steps, E]).
-        controller "greedy": the kernel evaluates algorithms/greedy.py:14-16 at launch; "given": `actions` holds."""
+        controller "greedy": the kernel evaluates algorithms/greedy.py:14-16 at launch; "given": `actions` holds.
+        lazy=True: (actions, WireResult) - see step()."""
         k = self.ticks_per_step if k is None else int(k)
         n_steps = int(n_steps)
+        if lazy:
+            act, _ = self.step_multi_wire(n_steps, actions, controller, k)
+            return act, WireResult(self, self._multi_wire[:n_steps])
         if getattr(self, "_multi_n", 0) < n_steps:
             E, I = self.num_envs, self.intersections
             self._multi = (self._host_array((n_steps, E, self.obs_len), np.float32),
@@ -261,6 +304,17 @@ class VecTrafficEnv(object):
         if k <= self.wire.max_k_ticks:
             return E * self.wire.stride
         return E * (self.obs_len * 4 + self.intersections * 4 + 1)
+
+    def host_float_dma(self):
+        """True when te_step(TE_HOST) delivers float outputs through the copy engine instead of expanding wire records
+        on the host (te_api.cu: float_dma; few host cores per GPU, or TE_HOST_FLOAT_DMA=1)."""
+        import os
+        ev = os.environ.get("TE_HOST_FLOAT_DMA")
+        if ev is not None:
+            return ev not in ("0", "")
+        n = C.c_int32(0)
+        self._L.te_device_count(C.byref(n))
+        return bool(n.value) and (os.cpu_count() or 1) // n.value < 8
 
     def host_path_note(self):
         return ("compact wire records of %d B per env (u8 passed / detected, f32 light / reward, u8 done) expanded on the "
