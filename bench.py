@@ -5,7 +5,8 @@ roads (L = 500 m), 16384 env instances per GPU, greedy light controller recomput
 actor steps (algorithms/greedy.py:13-16 with --spacing 3), Philox arrivals at the reference's
 stock --local_cars_per_sec 0.12, Remi(Repeater(10)) semantics, envs pre-rolled to the
 ring-capacity-bound steady state (see DESIGN.md "headline workload").  A step = one actor step
-(10 physics ticks unless a ring overflows) of every env = one te_step kernel launch.
+(10 physics ticks unless a ring overflows) of every env; the 3 actor steps a greedy decision holds for are ONE
+te_step_multi launch with the controller evaluated in the kernel (--no-multi: one te_step launch per step).
 
 After the timed region a `secondary` block puts the other BASELINE configs on the same record (every rank takes
 part, values are whole-job aggregates): the default 3x3 grid at 131072 envs per GPU (config 4: 2^20 envs at

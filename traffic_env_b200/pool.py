@@ -75,8 +75,13 @@ class EnvSlot(object):
 
 
 class EnvPool(object):
-    def __init__(self, num_slots, **vec_kwargs):
+    def __init__(self, num_slots, linger=150e-6, **vec_kwargs):
+        """linger: seconds a would-be leader waits ONCE for more actions when fewer slots are queued than the previous
+        launch served (bigger batches when all learners are fast; a slow learner costs the others at most this much
+        per step, never a whole round)."""
         vec_kwargs.setdefault("remi", True)
+        self._linger = float(linger)
+        self._last_batch = 1
         self.vec = VecTrafficEnv(num_envs=num_slots, **vec_kwargs)
         self.num_slots = num_slots
         self._cv = threading.Condition()
@@ -117,6 +122,7 @@ class EnvPool(object):
     def _submit(self, i, action):
         with self._cv:
             self._pending[i] = np.asarray(action).astype(bool).reshape(-1)
+            lingered = False
             while True:
                 if i in self._results:
                     res = self._results.pop(i)
@@ -124,8 +130,13 @@ class EnvPool(object):
                         raise res
                     return res
                 if not self._launching and i in self._pending:
+                    if not lingered and self._linger > 0 and len(self._pending) < self._last_batch:
+                        lingered = True
+                        self._cv.wait(self._linger)       # others may queue (or lead) meanwhile
+                        continue
                     batch, self._pending = self._pending, {}
                     self._launching = True
+                    self._last_batch = len(batch)
                     break
                 self._cv.wait()
         # leader: one masked launch for everything that was queued (the lock is released: others keep queueing)
