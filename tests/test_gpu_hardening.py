@@ -220,14 +220,17 @@ def test_wire_records_equal_float_outputs():
         assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] == d.stats()["vehicle_updates"]
 
 
-@pytest.mark.parametrize("m,n,L,E,lcps", [(3, 3, 250.0, 301, 0.5), (10, 10, 500.0, 6, 0.3), (2, 2, 120.0, 77, 0.9), (4, 4, 150.0, 33, 0.4)])
-def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps):
+@pytest.mark.parametrize("m,n,L,E,lcps,extra", [
+    (3, 3, 250.0, 301, 0.5, {}), (10, 10, 500.0, 6, 0.3, {}), (2, 2, 120.0, 77, 0.9, {}), (4, 4, 150.0, 33, 0.4, {}),
+    (3, 3, 250.0, 65, 0.5, {"learn_switch": True}), (3, 3, 250.0, 40, 0.15, {"validate": True}), (3, 3, 250.0, 50, 0.5, {"remi": False})])
+def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps, extra):
     """te_step_multi (n actor steps per launch, greedy controller evaluated in the kernel or a given action) produces,
     actor step by actor step, exactly what n te_step calls with the same action produce - host and device buffers -
     including overflow steps (early break) in the middle of a launch and an env count that leaves a partial CTA."""
     import torch
     from traffic_env_b200 import VecTrafficEnv
     kw = dict(m=m, n=n, length=L, num_envs=E, arrivals="philox", seed=11, local_cars_per_sec=lcps, ticks_per_step=10, remi=True)
+    kw.update(extra)
     a, b, d = VecTrafficEnv(**kw), VecTrafficEnv(**kw), VecTrafficEnv(**kw)
     I = m * n
     rng = np.random.RandomState(3)
@@ -241,7 +244,7 @@ def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps):
     d_rew = torch.zeros((NS, E, I), dtype=torch.float32, device=dev)
     d_done = torch.zeros((NS, E), dtype=torch.uint8, device=dev)
     saw_done = 0
-    for launch in range(14):
+    for launch in range(24 if extra.get("validate") else 14):
         ctrl = "greedy" if launch % 3 != 2 else "given"
         ns = NS if launch % 4 != 3 else 2
         if ctrl == "greedy":
@@ -273,33 +276,36 @@ def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps):
     sta, stb, std = a.stats(), b.stats(), d.stats()
     for k in ("ticks", "actor_steps", "vehicle_updates", "overflows", "cars_generated", "cars_exited"):
         assert sta[k] == stb[k] == std[k], k
-    assert saw_done > 0, "the test is meant to include overflow steps"
+    assert saw_done > 0 or extra.get("validate"), "the test is meant to include overflow steps"
+    if extra.get("validate"):
+        (ea, ta), (eb, tb), (ed, td) = a.trip_times(), b.trip_times(), d.trip_times()
+        assert len(ta) > 0 and ea.tobytes() == eb.tobytes() == ed.tobytes() and ta.tobytes() == tb.tobytes() == td.tobytes()
 
 
-def test_masked_step_touches_only_the_masked_envs():
+@pytest.mark.parametrize("m,n,L,E", [(3, 3, 250.0, 37), (10, 10, 500.0, 5), (2, 2, 100.0, 31)])
+def test_masked_step_touches_only_the_masked_envs(m, n, L, E):
     """te_step_masked: the masked envs advance exactly as the oracle does, the others keep their state, their arrival
     stream and their rows of the output arrays - for single envs of a shared CTA (two default-grid envs per CTA) too."""
     from traffic_env_b200 import VecTrafficEnv
     from traffic_env_b200.arrivals import gap_cdf
-    E, K = 37, 10
-    env = VecTrafficEnv(m=3, n=3, length=250.0, num_envs=E, arrivals="philox", seed=21, local_cars_per_sec=0.4,
+    K, I = 10, m * n
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, arrivals="philox", seed=21, local_cars_per_sec=0.4,
                         ticks_per_step=K, remi=True)
     rng = np.random.RandomState(2)
-    init = rng.randint(2, size=(E, 9))
+    init = rng.randint(2, size=(E, I))
     env.reset(init_phase=init)
     cdf = gap_cdf(env.cars_per_sec * 0.5)
     oracles = []
     for e in range(E):
-        o = OracleEnv(3, 3, 250.0, 0.5)
+        o = OracleEnv(m, n, L, 0.5)
         o.reset(init[e])
         o.philox_seed(21, e, cdf)
         oracles.append(o)
-    last = [None] * E
     for s in range(40):
         mask = rng.rand(E) < (0.5 if s % 5 else 0.08)
         if s == 7:
             mask[:] = False
-        act = rng.randint(2, size=(E, 9))
+        act = rng.randint(2, size=(E, I))
         sentinel = env._obs.copy()
         obs, rew, done = env.step_masked(act, mask)
         for e, o in enumerate(oracles):
