@@ -180,25 +180,24 @@ static StepVariant pick_fa(bool fa) {
   (void)fa;
   return {te_step_kernel<MAXT, MINB, VALIDATE, false, GROUPED>, MAXT};
 }
-// threads = rows of the CTA; grouped = several env instances per CTA (small grids, te_create)
+// threads = rows of the CTA; grouped = several env instances per CTA (small grids with the reference's archetype,
+// te_create).  20 instantiations of the step kernel: the set is kept small for the sake of build time.
 static StepVariant step_variant_for(int threads, bool validate, bool fa, bool grouped) {
   if (validate) {  // + the birth-tick plane in shared memory: one CTA fewer per SM
     if (threads <= 256) return pick_fa<256, 2, true, false>(false);
     if (threads <= 512) return pick_fa<512, 1, true, false>(false);
     return pick_fa<768, 1, true, false>(false);
   }
-  if (grouped) {
-    if (threads <= 64) return pick_fa<64, 16, false, true>(fa);
-    if (threads <= 96) return pick_fa<96, TE_MINB96, false, true>(fa);   // default 3x3 grid: two envs (2 x 48 roads) on three warps, 20 envs per SM
-    if (threads <= 128) return pick_fa<128, 8, false, true>(fa);
-    if (threads <= 160) return pick_fa<160, 6, false, true>(fa);
-    if (threads <= 192) return pick_fa<192, 5, false, true>(fa);
-    return pick_fa<256, 4, false, true>(fa);
+  if (grouped) {   // (only built for the fast archetype: te_create keeps G = 1 otherwise)
+    if (threads <= 64) return {te_step_kernel<64, 16, false, true, true>, 64};
+    if (threads <= 96) return {te_step_kernel<96, TE_MINB96, false, true, true>, 96};   // default 3x3 grid: two envs (2 x 48 roads) on three warps, 20 envs per SM
+    if (threads <= 128) return {te_step_kernel<128, 8, false, true, true>, 128};
+    if (threads <= 160) return {te_step_kernel<160, 6, false, true, true>, 160};
+    return {te_step_kernel<256, 4, false, true, true>, 256};
   }
   if (threads <= 64) return pick_fa<64, 16, false, false>(fa);
   if (threads <= 128) return pick_fa<128, 8, false, false>(fa);
   if (threads <= 256) return pick_fa<256, 4, false, false>(fa);
-  if (threads <= 448) return pick_fa<448, 2, false, false>(fa);
   if (threads <= 512) return pick_fa<512, 2, false, false>(fa);
   if (threads <= 768) return pick_fa<768, 1, false, false>(fa);
   return pick_fa<1024, 1, false, false>(fa);
@@ -503,7 +502,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
   const bool validate = (cfg->flags & TE_VALIDATE) != 0;
   h->G = 1; h->threads = h->Rp;
-  if (!validate && h->R < 128) {
+  if (!validate && h->R < 128 && fast_arch(h)) {
     double best = (double)(h->Rp - h->R) / h->Rp;
     for (int g = 2; g <= 4 && g * h->R <= 256; g++) {
       const int th = (g * h->R + 31) / 32 * 32;
@@ -513,7 +512,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   }
   if (const char *ev = getenv("TE_ENVS_PER_CTA")) {   // study knob
     const int g = atoi(ev);
-    if (g >= 1 && g <= 8 && g * h->R <= 1024 && !validate) { h->G = g; h->threads = g == 1 ? h->Rp : (g * h->R + 31) / 32 * 32; }
+    if (g >= 1 && g <= 8 && g * h->R <= 256 && !validate && fast_arch(h)) { h->G = g; h->threads = g == 1 ? h->Rp : (g * h->R + 31) / 32 * 32; }
   }
   h->warps = h->threads / GROUP_ROADS;
   p.G = h->G;

@@ -171,11 +171,11 @@ __host__ __device__ constexpr SmemLayout make_layout(int maxt, bool validate) {
   return L;
 }
 
-static_assert(make_layout(64, false).warp % 16 == 0 && make_layout(448, false).warp % 16 == 0 && make_layout(256, true).warp % 16 == 0 &&
+static_assert(make_layout(64, false).warp % 16 == 0 && make_layout(512, false).warp % 16 == 0 && make_layout(256, true).warp % 16 == 0 &&
               make_layout(1024, false).warp % 16 == 0 && make_layout(96, false).warp % 16 == 0 && make_layout(160, false).warp % 16 == 0 &&
-              make_layout(192, false).warp % 16 == 0 && WARP_AREA % 16 == 0 && make_layout(448, false).mbar % 8 == 0 &&
+              WARP_AREA % 16 == 0 && make_layout(512, false).mbar % 8 == 0 &&
               make_layout(96, false).mbar % 8 == 0 && make_layout(160, false).mbar % 8 == 0 &&
-              make_layout(448, false).vs % 16 == 0 && make_layout(448, true).ws % 16 == 0 && make_layout(64, false).cnt % 16 == 0,
+              make_layout(512, false).vs % 16 == 0 && make_layout(512, true).ws % 16 == 0 && make_layout(64, false).cnt % 16 == 0,
               "shared-memory layout alignment");
 // run-time tail, KT = ticks of the whole launch (nsteps * K):
 //   [G][cnt_stride] arrival counts | [G][KT + 1][2] Philox snapshots | [G][4] per-env words (ENVM_*)
