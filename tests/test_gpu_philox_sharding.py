@@ -219,8 +219,10 @@ def test_host_path_slices_equal_single_launch():
     assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] > 0
 
 
-@pytest.mark.parametrize("m,n,L,E,S,lcps", [(3, 3, 250.0, 48, 1200, 0.12), (10, 10, 500.0, 4, 330, 0.12), (5, 4, 150.0, 16, 400, 0.2)])
-def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps):
+@pytest.mark.parametrize("m,n,L,E,S,lcps,multi", [(3, 3, 250.0, 48, 1200, 0.12, False), (10, 10, 500.0, 4, 330, 0.12, False),
+                                                   (5, 4, 150.0, 16, 400, 0.2, False), (3, 3, 250.0, 49, 900, 0.12, True),
+                                                   (10, 10, 500.0, 3, 330, 0.12, True)])
+def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps, multi):
     """Long runs (up to 12000 ticks per env, no reset: the env keeps stepping after overflows, greedy lights every
     third step as in the bench) against the oracle on the same Philox stream: every actor step's observation,
     reward and done flag, and the final ring state, bit for bit.  Reaches the states a short run does not: dense
@@ -243,10 +245,14 @@ def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps):
     act = np.zeros((E, I), np.uint8)
     for s in range(S):
         if s % 3 == 0:
-            act = env.greedy_actions().copy()
+            if multi:   # the bench's scheme: the three actor steps of a greedy decision are one launch, controller in the kernel
+                act, obs3, rew3, done3 = env.step_multi(3, controller="greedy")
+                act = act.copy()
+            else:
+                act = env.greedy_actions().copy()
             for e, o in enumerate(oracles):   # the device controller == greedy.py:14-16 on the oracle's counts
                 assert (act[e] == (o.cars_on_roads().reshape(-1, 4).dot([1, 1, -1, -1]) < 0)).all(), (e, s)
-        obs, rew, done = env.step(act)
+        obs, rew, done = (obs3[s % 3], rew3[s % 3], done3[s % 3]) if multi else env.step(act)
         for e, o in enumerate(oracles):
             oo, orw, od = o.actor_step_philox(act[e].astype(np.int32), K, use_remi=True)
             assert obs[e].tobytes() == oo.tobytes() and rew[e].tobytes() == orw.tobytes() and bool(done[e]) == od, (e, s)
