@@ -166,6 +166,9 @@ struct te_handle {
 // x 2 CTAs, 101.7 KB each; 3x3 grid: 64 threads x 16 CTAs).
 typedef void (*step_kernel_t)(const StepParams);
 struct StepVariant { step_kernel_t fn; int maxt; };
+#ifndef TE_MINB512
+#define TE_MINB512 2
+#endif
 #ifndef TE_MINB96
 #define TE_MINB96 10   // CTAs per SM the 96-thread variant is compiled for (10: 64 registers; 9: 72)
 #endif
@@ -198,7 +201,7 @@ static StepVariant step_variant_for(int threads, bool validate, bool fa, bool gr
   if (threads <= 64) return pick_fa<64, 16, false, false>(fa);
   if (threads <= 128) return pick_fa<128, 8, false, false>(fa);
   if (threads <= 256) return pick_fa<256, 4, false, false>(fa);
-  if (threads <= 512) return pick_fa<512, 2, false, false>(fa);
+  if (threads <= 512) return pick_fa<512, TE_MINB512, false, false>(fa);
   if (threads <= 768) return pick_fa<768, 1, false, false>(fa);
   return pick_fa<1024, 1, false, false>(fa);
 }
