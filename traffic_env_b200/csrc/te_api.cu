@@ -527,7 +527,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
-  te_reset_kernel<<<cfg->num_envs, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
+  te_reset_kernel<<<(cfg->num_envs + RESET_ENVS_PER_CTA - 1) / RESET_ENVS_PER_CTA, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
   CUH(cudaGetLastError());
   CUH(cudaMemsetAsync(h->phase, 0, E * h->I, h->stream));
   // seed the arrival stream (draw 0 is the initial gap)
@@ -585,7 +585,7 @@ extern "C" int te_reset(te_handle *h, const uint8_t *env_mask, const uint8_t *in
     if (env_mask) { CU(cudaMemcpyAsync(h->d_mask, env_mask, E, cudaMemcpyHostToDevice, st)); dm = h->d_mask; }
     if (init_phase) { CU(cudaMemcpyAsync(h->d_init_phase, init_phase, E * h->I, cudaMemcpyHostToDevice, st)); dp = h->d_init_phase; }
   }
-  te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(h->base, dm, dp, 0);
+  te_reset_kernel<<<(h->cfg.num_envs + RESET_ENVS_PER_CTA - 1) / RESET_ENVS_PER_CTA, 128, 0, st>>>(h->base, dm, dp, 0);
   CU(cudaGetLastError());
   if (memspace == TE_HOST) CU(cudaStreamSynchronize(st));
   return 0;
@@ -706,7 +706,7 @@ static int launch_step(te_handle *h, const StepReq &q) {
     if (q.wire_only) { p.wire = (unsigned char *)q.obs; p.wire_stride = h->wire_stride; }
   }
   if (!raw && (h->cfg.flags & TE_AUTO_RESET)) {
-    te_reset_kernel<<<h->cfg.num_envs, 128, 0, st>>>(p, p.env_mask, nullptr, 1);
+    te_reset_kernel<<<(h->cfg.num_envs + RESET_ENVS_PER_CTA - 1) / RESET_ENVS_PER_CTA, 128, 0, st>>>(p, p.env_mask, nullptr, 1);
     CU(cudaGetLastError());
   }
   const bool validate = (h->cfg.flags & TE_VALIDATE) != 0;

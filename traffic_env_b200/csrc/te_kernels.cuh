@@ -914,44 +914,50 @@ __global__ void te_stage_kernel(const StepParams p, int validate) {
 }
 
 // TrafficEnv._reset (traffic_env.py:259-272) on the HBM state.  mask == nullptr: every env;
-// use_done != 0: envs whose last actor step ended the episode (TE_AUTO_RESET).
+// use_done != 0: of those, the envs whose last actor step ended the episode (TE_AUTO_RESET).
+// A CTA looks after RESET_ENVS_PER_CTA consecutive envs: the auto-reset pass runs before every actor step and usually
+// finds nothing to do, so it should not cost a CTA per env.
+constexpr int RESET_ENVS_PER_CTA = 16;
 __global__ void te_reset_kernel(StepParams p, const uint8_t *mask, const uint8_t *init_phase, int use_done) {
-  const int env = blockIdx.x;
-  EnvScalars *es = p.env + env;
-  bool doit = mask ? mask[env] != 0 : true;
-  if (use_done) doit = es->done || (p.episode_len > 0 && es->ep_step >= p.episode_len);
-  if (!doit) return;
   const int tid = threadIdx.x;
-  float *x = p.x + (size_t)env * p.Rp * CAP, *v = p.v + (size_t)env * p.Rp * CAP;
-  for (int road = tid; road < p.Rp; road += blockDim.x) {
-    const int det = (__float_as_uint(x[road * CAP]) >> 16) & 0xff;  // `detected` survives a reset
-    x[road * CAP] = __uint_as_float(pack_meta(1, 1, det));
-    v[road * CAP] = __int_as_float(0);
-    x[road * CAP + 1] = __int_as_float(0x7f800000);
-    v[road * CAP + 1] = 0.f;
-  }
-  for (int i = tid; i < p.I; i += blockDim.x) {
-    int ph;
-    if (init_phase) ph = init_phase[(size_t)env * p.I + i] != 0;
-    else {
-      uint32_t o[4];
-      philox4x32_10(es->reset_count, (uint32_t)(i >> 7), 1u, 0x5e5e7u, p.seed, (uint32_t)(p.env_id_base + env), o);
-      ph = (o[(i >> 5) & 3] >> (i & 31)) & 1;
+  const int env_end = min(p.num_envs, (int)(blockIdx.x + 1) * RESET_ENVS_PER_CTA);
+  for (int env = blockIdx.x * RESET_ENVS_PER_CTA; env < env_end; env++) {
+    EnvScalars *es = p.env + env;
+    bool doit = mask ? mask[env] != 0 : true;     // (CTA-uniform)
+    if (use_done) doit = doit && (es->done || (p.episode_len > 0 && es->ep_step >= p.episode_len));
+    if (!doit) continue;
+    float *x = p.x + (size_t)env * p.Rp * CAP, *v = p.v + (size_t)env * p.Rp * CAP;
+    for (int road = tid; road < p.Rp; road += blockDim.x) {
+      const int det = (__float_as_uint(x[road * CAP]) >> 16) & 0xff;  // `detected` survives a reset
+      x[road * CAP] = __uint_as_float(pack_meta(1, 1, det));
+      v[road * CAP] = __int_as_float(0);
+      x[road * CAP + 1] = __int_as_float(0x7f800000);
+      v[road * CAP + 1] = 0.f;
     }
-    p.phase[(size_t)env * p.I + i] = (uint8_t)ph;
-    p.elapsed[(size_t)env * p.I + i] = 0;
-    p.passed_dst[(size_t)env * p.I + i] = 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (es->ep_step > 0) {
-      atomicAdd(&p.stats->episodes, 1ull);
-      atomicAdd(&p.stats->return_sum, es->ep_ret);
-      atomicAdd(&p.stats->disc_return_sum, es->ep_disc);
+    const uint32_t reset_count = es->reset_count;
+    for (int i = tid; i < p.I; i += blockDim.x) {
+      int ph;
+      if (init_phase) ph = init_phase[(size_t)env * p.I + i] != 0;
+      else {
+        uint32_t o[4];
+        philox4x32_10(reset_count, (uint32_t)(i >> 7), 1u, 0x5e5e7u, p.seed, (uint32_t)(p.env_id_base + env), o);
+        ph = (o[(i >> 5) & 3] >> (i & 31)) & 1;
+      }
+      p.phase[(size_t)env * p.I + i] = (uint8_t)ph;
+      p.elapsed[(size_t)env * p.I + i] = 0;
+      p.passed_dst[(size_t)env * p.I + i] = 0;
     }
-    es->steps = 0.f; es->ep_step = 0; es->done = 0;
-    es->ep_ret = 0.0; es->ep_disc = 0.0; es->ep_mult = 1.0;
-    es->reset_count += 1;
+    __syncthreads();   // every thread has read reset_count / done before thread 0 rewrites the scalars
+    if (tid == 0) {
+      if (es->ep_step > 0) {
+        atomicAdd(&p.stats->episodes, 1ull);
+        atomicAdd(&p.stats->return_sum, es->ep_ret);
+        atomicAdd(&p.stats->disc_return_sum, es->ep_disc);
+      }
+      es->steps = 0.f; es->ep_step = 0; es->done = 0;
+      es->ep_ret = 0.0; es->ep_disc = 0.0; es->ep_mult = 1.0;
+      es->reset_count = reset_count + 1;
+    }
   }
 }
 
