@@ -97,12 +97,15 @@ def test_headline_steady_state_replay_16384():
     assert env.stats()["arrival_saturations"] == 0
 
 
-@pytest.mark.parametrize("m,n,L,E", [(10, 10, 60.0, 40), (13, 13, 60.0, 24), (15, 15, 60.0, 16)])
-def test_transfer_hazards_under_load(m, n, L, E):
-    """16-, 24- and 32-warp CTAs (512 / 768 / 1024-thread variants), many co-resident envs, short roads packed with cars
-    near the road end: most ticks pop two or more cars per road, so the parallel transfer phase keeps meeting the
-    slot-reuse hazard (-> strict-order fallback on that tick) and rings overflow (-> tick-stamped early break of the
-    fused step).  Fused K-tick steps against the oracle's tick loop; raw ticks are covered by test_gpu_fuzz_state."""
+@pytest.mark.parametrize("m,n,L,E,multi", [(10, 10, 60.0, 40, False), (13, 13, 60.0, 24, False), (15, 15, 60.0, 16, False),
+                                           (10, 10, 60.0, 24, True), (3, 3, 60.0, 90, True), (4, 4, 60.0, 31, True)])
+def test_transfer_hazards_under_load(m, n, L, E, multi):
+    """16-, 24- and 32-warp CTAs (512 / 768 / 1024-thread variants) and shared CTAs (3x3, 4x4), many co-resident envs,
+    short roads packed with cars near the road end: most ticks pop two or more cars per road, so the parallel transfer
+    phase keeps meeting the slot-reuse hazard (-> strict-order fallback on that tick) and rings overflow (-> tick-stamped
+    early break of the fused step).  Fused K-tick steps - one per launch, or two per launch (te_step_multi: the
+    ordered-transfer stamps then have to survive the step boundary) - against the oracle's tick loop; raw ticks are
+    covered by test_gpu_fuzz_state."""
     from traffic_env_b200 import VecTrafficEnv
     rng = np.random.RandomState(31 * m + n)
     K, S = 6, 4
@@ -121,9 +124,16 @@ def test_transfer_hazards_under_load(m, n, L, E):
     cursor = np.zeros(E, np.int64)         # arrival-process tick of each env (advances by the ticks actually run)
     multi_pop = breaks = 0
     for s in range(S):
-        act = rng.randint(0, 2, size=(E, I))
-        obs, rew, done = env.step(act)
-        st = env.get_state()
+        if multi and s % 2 == 1:
+            obs, rew, done = obs2[1], rew2[1], done2[1]          # second actor step of the launch, same action
+        else:
+            act = rng.randint(0, 2, size=(E, I))
+            if multi:
+                _, obs2, rew2, done2 = env.step_multi(2, actions=act, controller="given")
+                obs, rew, done = obs2[0], rew2[0], done2[0]
+            else:
+                obs, rew, done = env.step(act)
+        st = env.get_state() if (not multi or s % 2 == 1) else None    # (the state is that after the whole launch)
         for e, o in enumerate(oracles):
             passed = np.zeros(r, np.float32)
             od = False
@@ -143,13 +153,14 @@ def test_transfer_hazards_under_load(m, n, L, E):
             assert obs[e, :r].tobytes() == passed.tobytes(), tag + " passed"
             assert (obs[e, r:2 * r] == o.detected).all(), tag + " detected"
             assert rew[e].tobytes() == orw.tobytes(), tag + " reward"
-            assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all(), tag + " rings"
-            gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
-            ox, ov = o.live_state()
-            assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), tag + " car state"
+            if st is not None:
+                assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all(), tag + " rings"
+                gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+                ox, ov = o.live_state()
+                assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), tag + " car state"
     stats = env.stats()
-    assert multi_pop > 5 * E and breaks > 0
-    assert stats["seq_fallback_ticks"] > E // 4, "the ordered-transfer fallback is meant to fire on most envs"
+    assert multi_pop > E * R // 200 and breaks > 0
+    assert stats["seq_fallback_ticks"] > (E // 4 if R > 200 else 0), "the ordered-transfer fallback is meant to fire"
     assert stats["overflows"] == sum(o.overflows for o in oracles)
 
 
