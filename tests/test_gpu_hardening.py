@@ -249,7 +249,7 @@ def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps, extra):
     for env in (a, b, d):
         env.reset(init_phase=init)
     dev = torch.device("cuda", 0)
-    NS = 3
+    NS = 6 if (m, n) == (4, 4) else 3          # 6 x 10 ticks: close to the 64-tick limit of one launch
     d_act = torch.zeros((E, I), dtype=torch.uint8, device=dev)
     d_obs = torch.zeros((NS, E, a.obs_len), dtype=torch.float32, device=dev)
     d_rew = torch.zeros((NS, E, I), dtype=torch.float32, device=dev)
@@ -258,6 +258,8 @@ def test_multi_step_launch_equals_single_steps(m, n, L, E, lcps, extra):
     for launch in range(24 if extra.get("validate") else 14):
         ctrl = "greedy" if launch % 3 != 2 else "given"
         ns = NS if launch % 4 != 3 else 2
+        if launch == 5:
+            ns = 1
         if ctrl == "greedy":
             act = a.greedy_actions().copy()
             act_b, obs_b, rew_b, done_b = b.step_multi(ns, controller="greedy")
@@ -389,3 +391,19 @@ def test_lazy_results_and_both_host_transports(monkeypatch):
             assert res.obs.tobytes() == oa.tobytes() and res.reward.tobytes() == ra.tobytes() and (res.done == da).all(), s
             assert res.obs_of([3, 4], step=2).tobytes() == oa[2, [3, 4]].tobytes()
     assert a.stats()["vehicle_updates"] == b.stats()["vehicle_updates"] == lz.stats()["vehicle_updates"] > 0
+
+
+def test_multi_step_argument_errors():
+    from traffic_env_b200 import TrafficB200Error, VecTrafficEnv
+    env = VecTrafficEnv(m=3, n=3, num_envs=8, arrivals="philox", ticks_per_step=10)
+    with pytest.raises(TrafficB200Error, match="n_steps"):
+        env.step_multi(7, controller="greedy")              # 70 ticks > 64 per launch
+    with pytest.raises(TrafficB200Error, match="n_steps"):
+        env.step_multi(0, controller="greedy")
+    act, obs, rew, done = env.step_multi(6, controller="greedy")
+    assert obs.shape == (6, 8, 81) and rew.shape == (6, 8, 9) and done.shape == (6, 8)
+    auto = VecTrafficEnv(m=3, n=3, num_envs=8, arrivals="philox", ticks_per_step=10, auto_reset=True, episode_len=5)
+    with pytest.raises(TrafficB200Error, match="TE_AUTO_RESET"):
+        auto.step_multi(3, controller="greedy")
+    o, r, d = auto.step(np.zeros((8, 9)))                   # single steps are what such a handle is for
+    assert o.shape == (8, 81)
