@@ -10,5 +10,11 @@ for w in (4, 8, 12, 16, 20, 24, 28, 32):
     # w/4 warps per scheduler, each issuing one update of 32 cars per L cycles: r = 148 * w * 32 / L * clk
     L = 148 * w * 32 * 1.965e9 / r
     print("warps/SM %2d  %.3e updates/s  %.3f updates/clk/SM  cycles per warp-update %.0f" % (w, r, per_clk_sm, L))
+os.environ["TE_PEAK_ILP2"] = "1"
+for w in (4, 8, 12, 16, 20, 24, 32):
+    os.environ["TE_PEAK_WARPS_PER_SM"] = str(w)
+    r = idm_arithmetic_peak(iters=4000)
+    print("two independent cars per lane, warps/SM %2d  %.3e updates/s" % (w, r))
+del os.environ["TE_PEAK_ILP2"]
 del os.environ["TE_PEAK_WARPS_PER_SM"]
 print("full occupancy: %.3e" % idm_arithmetic_peak(iters=4000))

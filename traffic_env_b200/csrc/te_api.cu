@@ -1113,6 +1113,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
   // latency study: TE_PEAK_WARPS_PER_SM = w runs w warps per SM (one CTA of w warps per SM) instead
+  const int ilp2 = getenv("TE_PEAK_ILP2") ? 1 : 0;   // latency study: two independent cars per lane
   if (const char *ev = getenv("TE_PEAK_WARPS_PER_SM")) { const int w = atoi(ev); if (w >= 1 && w <= 32) { threads = 32 * w; blocks = sms; } }
   float *sink = nullptr;
   CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
@@ -1121,15 +1122,15 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaMemcpy(dc, &c, sizeof(IdmConst), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters / 4 + 1, sink);  // warm-up
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters / 4 + 1, sink, ilp2);  // warm-up
   CU(cudaEventRecord(e0));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters, sink);
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters, sink, ilp2);
   CU(cudaEventRecord(e1));
   CU(cudaEventSynchronize(e1));
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  *updates_per_sec = (double)threads * blocks * iters / (ms * 1e-3);
+  *updates_per_sec = (double)threads * blocks * iters * (ilp2 ? 2 : 1) / (ms * 1e-3);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink); cudaFree(dc);
   return 0;
 }

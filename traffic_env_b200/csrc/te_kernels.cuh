@@ -1022,7 +1022,7 @@ __global__ void te_test_idm_kernel(IdmConst c, const IdmConst *cg, const float *
 }
 // Arithmetic-only ceiling: every lane runs `iters` dependent IDM updates of one car behind a leader that
 // drives at constant speed (registers only, full-precision path: both divisions and powf every time).
-__global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, float *sink) {
+__global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, float *sink, int ilp2) {
   __shared__ PowfTables tabs;
   for (int i = threadIdx.x; i < (int)(sizeof(PowfTables) / 8); i += blockDim.x)
     reinterpret_cast<unsigned long long *>(&tabs)[i] = reinterpret_cast<const unsigned long long *>(&g_powf_tables)[i];
@@ -1031,6 +1031,17 @@ __global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, fl
   float x = 0.f, v = 5.f + 0.001f * (float)(gid & 1023);
   float xl = 30.f + 0.01f * (float)(gid & 255);
   const float vl = 9.f, step = __fmul_rn(vl, c.rate);
+  if (ilp2) {
+    // latency study: TWO independent cars per lane (one straight-line block: the compiler interleaves the chains)
+    float x2 = 1.f, v2 = 6.f + 0.001f * (float)(gid & 511), xl2 = 40.f + 0.01f * (float)(gid & 127);
+    for (int i = 0; i < iters; i++) {
+      idm_update<false>(c, cg, &tabs, xl, vl, c.len, x, v);
+      idm_update<false>(c, cg, &tabs, xl2, vl, c.len, x2, v2);
+      xl = __fadd_rn(xl, step); xl2 = __fadd_rn(xl2, step);
+    }
+    sink[gid] = x + v + x2 + v2;
+    return;
+  }
   for (int i = 0; i < iters; i++) {
     idm_update<false>(c, cg, &tabs, xl, vl, c.len, x, v);
     xl = __fadd_rn(xl, step);
