@@ -49,7 +49,7 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "traffic_env_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libtraffic_oracle" not in txt, f
 
