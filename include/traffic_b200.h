@@ -154,6 +154,22 @@ enum te_controller { TE_CTRL_GIVEN = 0, TE_CTRL_GREEDY = 1 };
 int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks, float *obs,
                   float *reward, uint8_t *done, int memspace, void *stream);
 
+/* Env-slot pool for learner threads (a3c.py:66-72: FLAGS.threads workers, each stepping its own env): te_pool_step
+   queues slot `slot`'s action (uint8[I]) and blocks until that slot has been advanced by one actor step of k_ticks ticks;
+   whichever caller finds no launch in flight becomes the leader and advances every slot queued so far with one
+   te_step_masked launch - no lock-step round, a slow learner only delays itself (a would-be leader waits once, at most
+   linger_us, when fewer slots are queued than the previous launch served).  Thread-safe; one pool per handle, and the
+   handle must not be stepped directly while a pool uses it.  te_pool_reset: TrafficEnv._reset of one slot with the
+   given initial phases (uint8[I]); te_pool_cars: cars_on_roads of one slot (int32[R]). */
+typedef struct te_pool te_pool;
+int te_pool_create(te_handle *h, int32_t k_ticks, int32_t linger_us, te_pool **out);
+int te_pool_destroy(te_pool *p);
+int te_pool_step(te_pool *p, int32_t slot, const uint8_t *action, float *obs, float *reward, uint8_t *done);
+int te_pool_reset(te_pool *p, int32_t slot, const uint8_t *init_phase);
+int te_pool_cars(te_pool *p, int32_t slot, int32_t *out);
+int te_pool_counters(te_pool *p, uint64_t *launches, uint64_t *stepped);
+const char *te_pool_last_error(te_pool *p);
+
 /* The same actor step with its results as compact WIRE RECORDS, one per env (what te_step(TE_HOST) moves over PCIe
    internally): u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done, `stride` bytes apart
    (te_wire_layout) - 2.5 x fewer bytes than the float observation; the integer-valued observation entries

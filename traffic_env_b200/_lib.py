@@ -20,7 +20,8 @@ TE_CTRL_GIVEN, TE_CTRL_GREEDY = 0, 1
 
 EXPORTS = [
     "te_default_config", "te_device_count", "te_create", "te_destroy", "te_get_dims", "te_last_error", "te_get_topology",
-    "te_reset", "te_set_arrivals", "te_step", "te_step_masked", "te_step_multi", "te_step_multi_wire", "te_step_wire", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
+    "te_reset", "te_set_arrivals", "te_step", "te_step_masked", "te_step_multi", "te_step_multi_wire", "te_step_wire",
+    "te_pool_create", "te_pool_destroy", "te_pool_step", "te_pool_reset", "te_pool_cars", "te_pool_counters", "te_pool_last_error", "te_wire_layout", "te_expand_wire", "te_step_raw", "te_remi_reward", "te_cars_on_roads",
     "te_greedy_actions", "te_get_state", "te_set_state", "te_get_stats", "te_get_trip_times",
     "te_synchronize", "te_host_alloc", "te_host_free", "te_last_kernel_ms", "te_stage_bandwidth", "te_idm_peak", "te_test_powf", "te_test_idm", "te_test_powf4_exhaustive", "te_test_fdiv_const_exhaustive", "te_test_philox",
 ]
@@ -88,6 +89,14 @@ def load():
     L.te_step_masked.argtypes = [vp, vp, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_multi.argtypes = [vp, i32, i32, vp, i32, vp, vp, vp, C.c_int, vp]
     L.te_step_multi_wire.argtypes = [vp, i32, i32, vp, i32, vp, C.c_int, vp]
+    L.te_pool_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.te_pool_destroy.argtypes = [vp]
+    L.te_pool_step.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.te_pool_reset.argtypes = [vp, i32, vp]
+    L.te_pool_cars.argtypes = [vp, i32, vp]
+    L.te_pool_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.te_pool_last_error.argtypes = [vp]
+    L.te_pool_last_error.restype = C.c_char_p
     L.te_wire_layout.argtypes = [vp, C.POINTER(TeWireLayout)]
     L.te_expand_wire.argtypes = [vp, vp, i32, vp, vp, vp]
     L.te_remi_reward.argtypes = [vp, vp, C.c_int, vp]
@@ -109,7 +118,7 @@ def load():
     L.te_test_fdiv_const_exhaustive.argtypes = [C.c_int, C.c_float, vp]
     L.te_test_philox.argtypes = [C.c_int, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("te_default_config", "te_last_error"):
+        if name not in ("te_default_config", "te_last_error", "te_pool_last_error"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

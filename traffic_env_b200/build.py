@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libtraffic_b200.so")
-SOURCES = ["te_api.cu", "te_host.cpp"]
+SOURCES = ["te_api.cu", "te_host.cpp", "te_pool.cpp"]
 HEADERS = ["te_kernels.cuh", "te_math.cuh", os.path.join("..", "..", "include", "traffic_b200.h")]
 
 

@@ -10,13 +10,12 @@ No slot waits for another slot's owner: a step() call queues its action; whichev
 flight becomes the leader, takes EVERY action queued so far (at least its own) and advances exactly those slots
 with one te_step_masked launch (the other slots' state and arrival streams are untouched); callers that arrive
 while a launch is in flight are served by the next one.  A slow learner thread therefore only delays itself, and
-the batch size adapts to how many threads are ready.
+the batch size adapts to how many threads are ready.  The queue, the leader election and the launch live in the
+library (te_pool_step, csrc/te_pool.cpp) and run without the GIL.
 
 Semantics per slot are those of Remi(Repeater(K)) on the reference env (traffic_test.py:27-64): reset() is
 TrafficEnv._reset followed by one step with a random action whose observation is returned (:34-36).
 """
-import threading
-
 import numpy as np
 
 from .vec_env import VecTrafficEnv
@@ -75,88 +74,79 @@ class EnvSlot(object):
 
 
 class EnvPool(object):
+    """num_slots env instances in one batched handle, stepped through the library's slot pool (te_pool_*,
+    csrc/te_pool.cpp): queueing, leader election and the masked launch all run outside the Python GIL."""
+
     def __init__(self, num_slots, linger=150e-6, **vec_kwargs):
         """linger: seconds a would-be leader waits ONCE for more actions when fewer slots are queued than the previous
         launch served (bigger batches when all learners are fast; a slow learner costs the others at most this much
         per step, never a whole round)."""
+        import ctypes as C
+        from ._lib import check
         vec_kwargs.setdefault("remi", True)
-        self._linger = float(linger)
-        self._last_batch = 1
         self.vec = VecTrafficEnv(num_envs=num_slots, **vec_kwargs)
         self.num_slots = num_slots
-        self._cv = threading.Condition()
-        self._pending = {}                        # slot -> action, queued for the next launch
-        self._results = {}                        # slot -> (obs, reward, done, info) of its last step, until fetched
-        self._launching = False
-        self._actions = np.zeros((num_slots, self.vec.intersections), np.uint8)
-        self._mask = np.zeros(num_slots, np.uint8)
+        self._C, self._L = C, self.vec._L
+        self._p = C.c_void_p()
+        check(self._L.te_pool_create(self.vec._h, self.vec.ticks_per_step, int(round(linger * 1e6)), C.byref(self._p)))
         self._slots = [EnvSlot(self, i) for i in range(num_slots)]
-        self.launches = 0
-        self.stepped = 0                          # env actor steps served (sum of batch sizes)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self._L.te_pool_destroy(self._p)
+            self._p = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def slot(self, i):
         return self._slots[i]
 
+    def _fail(self):
+        from ._lib import TrafficB200Error
+        raise TrafficB200Error(self._L.te_pool_last_error(self._p).decode("utf-8", "replace"))
+
+    @property
+    def launches(self):
+        return self._counters()[0]
+
+    @property
+    def stepped(self):
+        """env actor steps served (sum of the batch sizes)"""
+        return self._counters()[1]
+
+    def _counters(self):
+        a, b = self._C.c_uint64(), self._C.c_uint64()
+        self._L.te_pool_counters(self._p, self._C.byref(a), self._C.byref(b))
+        return a.value, b.value
+
     # ---- called by the slots
     def _reset_slot(self, i, init_phase=None):
-        with self._cv:
-            while self._launching:                # the device state of slot i must not change under a launch
-                self._cv.wait()
-            mask = np.zeros(self.num_slots, np.uint8)
-            mask[i] = 1
-            phases = np.zeros((self.num_slots, self.vec.intersections), np.uint8)
-            phases[i] = np.random.randint(2, size=self.vec.intersections) if init_phase is None else np.asarray(init_phase).astype(bool)
-            self.vec.reset(mask=mask, init_phase=phases)
+        I = self.vec.intersections
+        ph = np.random.randint(2, size=I) if init_phase is None else np.asarray(init_phase).astype(bool)
+        ph = np.ascontiguousarray(ph, dtype=np.uint8)
+        if self._L.te_pool_reset(self._p, int(i), ph.ctypes.data) < 0:
+            self._fail()
 
     def _cars(self, i):
-        with self._cv:
-            while self._launching:
-                self._cv.wait()
-            return self.vec.cars_on_roads()[i].copy()
+        out = np.empty(self.vec.roads, np.int32)
+        if self._L.te_pool_cars(self._p, int(i), out.ctypes.data) < 0:
+            self._fail()
+        c = out[:self.vec.train_roads]
+        return np.transpose(c.reshape(4, self.vec.m, self.vec.n), (1, 2, 0))
 
     def leave(self, i):
         """The owner of slot i stops stepping (kept for API compatibility: nobody waits for it anyway)."""
-        with self._cv:
-            self._pending.pop(i, None)
 
     def _submit(self, i, action):
-        with self._cv:
-            self._pending[i] = np.asarray(action).astype(bool).reshape(-1)
-            lingered = False
-            while True:
-                if i in self._results:
-                    res = self._results.pop(i)
-                    if isinstance(res, BaseException):
-                        raise res
-                    return res
-                if not self._launching and i in self._pending:
-                    if not lingered and self._linger > 0 and len(self._pending) < self._last_batch:
-                        lingered = True
-                        self._cv.wait(self._linger)       # others may queue (or lead) meanwhile
-                        continue
-                    batch, self._pending = self._pending, {}
-                    self._launching = True
-                    self._last_batch = len(batch)
-                    break
-                self._cv.wait()
-        # leader: one masked launch for everything that was queued (the lock is released: others keep queueing)
-        out = None
-        try:
-            self._mask[:] = 0
-            for j, a in batch.items():
-                self._actions[j] = a
-                self._mask[j] = 1
-            obs, rew, done = self.vec.step_masked(self._actions, self._mask)
-            out = {j: (obs[j].copy(), rew[j].copy(), bool(done[j]), None) for j in batch}
-        except BaseException as ex:               # every caller of the failed batch gets the error, nobody hangs
-            out = {j: ex for j in batch}
-        with self._cv:
-            self._launching = False
-            self.launches += 1
-            self.stepped += len(batch)
-            self._results.update(out)
-            self._cv.notify_all()
-            mine = self._results.pop(i)
-        if isinstance(mine, BaseException):
-            raise mine
-        return mine
+        v = self.vec
+        a = np.ascontiguousarray(np.asarray(action).astype(bool).reshape(-1), dtype=np.uint8)
+        obs = np.empty(v.obs_len, np.float32)
+        rew = np.empty(v.intersections, np.float32)
+        done = self._C.c_uint8(0)
+        if self._L.te_pool_step(self._p, int(i), a.ctypes.data, obs.ctypes.data, rew.ctypes.data, self._C.byref(done)) < 0:
+            self._fail()
+        return obs, rew, bool(done.value), None
