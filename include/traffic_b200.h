@@ -212,6 +212,14 @@ int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *
                  const float *x, const float *v, const int32_t *obs, const int32_t *waiting,
                  const uint8_t *passed_dst, const float *steps);
 
+/* *tame = 1 while the handle runs the unchecked arithmetic: its archetype is inside the supported ranges and every car ever
+   handed to te_set_state was tame - x finite with |x| < 2^40, v zero or in [2^-100, *v_cap], *v_cap = twice the fastest
+   speed the archetype's dynamics can produce.  Tame state stays tame under the step, and no operand of the IDM update can
+   then leave the domain on which its fast sequences are exact, so the per-car validity predicate and the generic
+   fallback are not compiled into the kernels that run.  One wild car in te_set_state switches the
+   handle to the checked kernels for good.  v_cap may be NULL. */
+int te_is_tame(const te_handle *h, int32_t *tame, float *v_cap);
+
 /* Counters since te_create (device -> host; synchronises the device). */
 int te_get_stats(te_handle *h, te_stats *out);
 
@@ -249,6 +257,9 @@ int te_test_powf(int device, const float *x, float y, float *out, int64_t n);
 /* One IDM update per element (traffic_env.py:50-62): follower (x,v) behind leader (xl,vl,ll). */
 int te_test_idm(int device, float rate, const float *archetype, const float *xl, const float *vl, const float *ll,
                 const float *x, const float *v, float *x_out, float *v_out, int64_t n);
+/* The same through the unchecked form (valid for tame operands and the reference's archetype flags only). */
+int te_test_idm_tame(int device, float rate, const float *archetype, const float *xl, const float *vl, const float *ll,
+                     const float *x, const float *v, float *x_out, float *v_out, int64_t n);
 /* powf(r, 4) over every non-negative finite float r: out[0] = #r where RN_f32((r*r)*(r*r)) differs from the
    glibc algorithm, out[1] = largest distance (2^-52 units of the significand) of such a product from the float
    rounding boundary, out[2] = #r the shortcut filter with threshold tau declines, out[3] = #r it accepts although

@@ -407,3 +407,57 @@ def test_multi_step_argument_errors():
         auto.step_multi(3, controller="greedy")
     o, r, d = auto.step(np.zeros((8, 9)))                   # single steps are what such a handle is for
     assert o.shape == (8, 81)
+
+
+@pytest.mark.parametrize("m,n,L,E", [(3, 3, 250.0, 66), (10, 10, 120.0, 6), (1, 1, 60.0, 8)])
+def test_wild_car_moves_the_handle_to_the_checked_kernels(m, n, L, E):
+    """A handle runs the kernels without the per-car validity predicate only while every car it was ever given is tame
+    (te_is_tame, include/traffic_b200.h).  Tame random states first (is_tame stays set, two shared-CTA envs per CTA on
+    the 3x3 grid), then the same states with a few cars at speeds outside the tame range - float products that round
+    (1e-35, 3e-31, subnormal 1e-42: the generic routine decides) or above the handle's speed cap (200 m/s): the handle
+    must leave the tame mode and every tick must still match the oracle bit for bit.  (Speeds that overflow to NaN state
+    are compared - NaN payloads aside - at the level of the update in test_gpu_math.py::test_idm_adversarial_operands.)"""
+    from traffic_env_b200 import VecTrafficEnv
+    rng = np.random.RandomState(5 * m + n)
+    T = 6
+    env = VecTrafficEnv(m=m, n=n, length=L, num_envs=E, arrivals="injected", remi=False)
+    R, r, I = env.roads, env.train_roads, env.intersections
+    assert env.is_tame()
+    for wild in (False, True):
+        states = [random_env_state(rng, R, r, I, L, True) for _ in range(E)]
+        nwild = 0
+        if wild:
+            for st in states[::2]:
+                for rd in rng.choice(R, size=min(R, 6), replace=False):
+                    ld, lc = int(st["leading"][rd]), int(st["lastcar"][rd])
+                    if ld == lc:
+                        continue
+                    sl = 1 if ld + 1 >= 20 else ld + 1
+                    st["v"][rd, sl] = np.float32(rng.choice([1e-35, 1e-42, 200.0, 3e-31]))
+                    nwild += 1
+            assert nwild > 0
+        scheds = [[list(rng.choice(env.entrypoints, size=rng.randint(0, 3))) for _ in range(T)] for _ in range(E)]
+        env.set_arrivals(scheds, first_tick=T if wild else 0)     # (the envs' arrival clocks are at T after the first pass)
+        env.set_state({k: np.stack([s[k] for s in states]) for k in states[0]} | {"steps": np.zeros(E, np.float32)})
+        assert env.is_tame() == (not wild)
+        oracles = []
+        for e in range(E):
+            o = OracleEnv(m, n, L, 0.5)
+            load_oracle(o, states[e])
+            oracles.append(o)
+        for t in range(T):
+            act = rng.randint(0, 2, size=(E, I))
+            obs, rew, done = env.step_raw(act)
+            st = env.get_state()
+            for e, o in enumerate(oracles):
+                od = o.step(act[e], scheds[e][t])
+                tag = "wild %s env %d tick %d" % (wild, e, t)
+                assert (st["leading"][e] == o.leading).all() and (st["lastcar"][e] == o.lastcar).all(), tag + " rings"
+                assert (obs[e] == o.obs).all(), tag + " obs"
+                assert rew[e].tobytes() == o.rewards.tobytes(), tag + " rewards"
+                assert bool(done[e]) == od, tag + " done"
+                gx, gv = live_walk(st["leading"][e], st["lastcar"][e], st["x"][e], st["v"][e])
+                ox, ov = o.live_state()
+                assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), tag + " car state"
+    # a tame state afterwards does not bring the unchecked kernels back (cars given earlier may still be on the roads)
+    assert not env.is_tame()

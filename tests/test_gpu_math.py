@@ -208,3 +208,65 @@ def test_idm_pow2_forms_agree_with_conversions_and_oracle():
         ox, ov = orc.sim_bulk(rate, xl, vl, ll, x, v, arch)
         assert same_bits(a[0], b[0]).all() and same_bits(a[1], b[1]).all()
         assert same_bits(a[0], ox).all() and same_bits(a[1], ov).all()
+
+
+def gpu_idm_tame(rate, arch, xl, vl, ll, x, v):
+    L, m = _lib()
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (xl, vl, ll, x, v)]
+    a = np.ascontiguousarray(arch, np.float32)
+    xo, vo = np.empty_like(arrs[0]), np.empty_like(arrs[0])
+    m.check(L.te_test_idm_tame(0, float(rate), a.ctypes.data, *[t.ctypes.data for t in arrs], xo.ctypes.data,
+                               vo.ctypes.data, arrs[0].size))
+    return xo, vo
+
+
+def test_idm_unchecked_form_on_tame_operands():
+    """The form the step kernels run while the handle is tame (idm_update<true, false>: no validity predicate, no generic
+    fallback) against the checked form and the oracle, over the whole tame domain and its edges: speeds of 0, 2^-100,
+    the handle's speed cap (twice the fastest speed of the dynamics) and log-uniform in between, positions up to 2^40 in magnitude, gaps from overlapping (negative) through
+    zero and the -1e-8 neighbourhood to 2^40 and the free road (+inf leader), leader lengths 0 and up to 2^19; and that
+    the results are tame again (closed domain: what the kernel relies on tick after tick)."""
+    rng = np.random.RandomState(77)
+    n = 3_000_000
+    arch = np.array([0.0, 11.11, 4.0, 3.0, 4.0, 13.89, 6.0, 2.0, 1.0, 0.0], np.float32)
+    lo, hi = np.float32(2.0 ** -100), np.float32(2.0 * (13.89 + 3.0 * 0.5))     # tame_archetype's cap
+    v = np.exp(rng.uniform(np.log(float(lo)), np.log(float(hi)), n)).astype(np.float32)
+    v = np.clip(v, lo, hi)
+    v[: n // 2] = rng.uniform(0, 30, n // 2).astype(np.float32)
+    v[n // 2: n // 2 + 20000] = 0.0
+    v[n // 2 + 20000: n // 2 + 30000] = lo
+    v[n // 2 + 30000: n // 2 + 40000] = hi
+    v[n // 2 + 40000: n // 2 + 60000] = np.float32(13.89) * (1 + rng.randint(-3, 4, 20000) * np.float32(2.0 ** -23))
+    vl = np.where(rng.rand(n) < 0.3, 0, np.exp(rng.uniform(np.log(float(lo)), np.log(float(hi)), n))).astype(np.float32)
+    vl[: n // 2] = np.where(rng.rand(n // 2) < 0.3, 0, rng.uniform(0, 30, n // 2)).astype(np.float32)
+    x = (rng.uniform(-1, 1, n) * np.exp(rng.uniform(np.log(1e-3), np.log(2.0 ** 39), n))).astype(np.float32)
+    x[: n // 2] = rng.uniform(-50, 600, n // 2).astype(np.float32)
+    ll = np.where(rng.rand(n) < 0.3, 0, 4).astype(np.float32)
+    ll[-5000:] = np.float32(2.0 ** 19)
+    gap = np.exp(rng.uniform(np.log(1e-9), np.log(2.0 ** 39), n)) * np.where(rng.rand(n) < 0.15, -1, 1)
+    gap[: n // 4] = rng.uniform(-2, 60, n // 4)
+    xl = (x.astype(np.float64) + ll + gap).astype(np.float32)
+    k = 200000
+    xl[k: k + 50000] = np.inf                                   # free road
+    xl[k + 50000: k + 100000] = x[k + 50000: k + 100000] + ll[k + 50000: k + 100000]      # gap exactly zero (when exact)
+    v[k + 100000: k + 150000] = np.where(rng.rand(50000) < 0.5, hi, v[k + 100000: k + 150000])   # largest s_star there
+    vl[k + 100000: k + 150000] = np.where(rng.rand(50000) < 0.5, 0, vl[k + 100000: k + 150000])
+    near = (x[k + 100000: k + 150000].astype(np.float64) + ll[k + 100000: k + 150000] - 1e-8)
+    xl[k + 100000: k + 150000] = near.astype(np.float32)        # s + 1e-8 as close to zero as floats allow
+    # the worst case of the closure argument: gap exactly -RN_f32(1e-8) (|s + 1e-8| = 6.08e-17, the largest quotient) and
+    # its float neighbours, at the speed cap behind a standing leader (the largest s_star)
+    w = slice(k + 150000, k + 153000)
+    x[w], ll[w], v[w], vl[w] = 0.0, 0.0, hi, 0.0
+    e8 = np.float32(1e-8)
+    xl[w] = np.tile(np.array([-e8, np.nextafter(-e8, np.float32(0)), np.nextafter(-e8, np.float32(-1))], np.float32), 1000)
+    v[k + 151500: k + 153000] = rng.uniform(0, float(hi), 1500).astype(np.float32)
+    xl = np.where(np.isfinite(xl) & (np.abs(xl) >= 2.0 ** 40), np.float32(2.0 ** 39), xl).astype(np.float32)
+    ux, uv = gpu_idm_tame(0.5, arch, xl, vl, ll, x, v)
+    cx, cv = gpu_idm(0.5, arch, xl, vl, ll, x, v)
+    ox, ov = orc.sim_bulk(0.5, xl, vl, ll, x, v, arch)
+    assert same_bits(cx, ox).all() and same_bits(cv, ov).all()
+    bx, bv = ~same_bits(ux, ox), ~same_bits(uv, ov)
+    assert not bx.any() and not bv.any(), "x mismatches %d, v mismatches %d" % (bx.sum(), bv.sum())
+    assert np.isfinite(ux).all() and (np.abs(ux) < 2.0 ** 40 + 2.0 ** 21).all()
+    assert ((uv == 0) | ((uv >= lo) & (uv <= hi))).all() and not np.signbit(uv).any()
+    assert (uv <= np.maximum(v, np.float32(13.89 + 3.0 * 0.5)) * np.float32(1 + 1e-6)).all()

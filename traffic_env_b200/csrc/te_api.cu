@@ -155,6 +155,8 @@ struct te_handle {
   // wire path of the host API
   unsigned char *d_wire, *h_wire;   // [E][wire_stride] device / page-locked host
   int wire_stride, host_slices, wire_steps, float_steps;
+  bool tame;             // every car the device has seen is tame (te_math.cuh: CHECKED = false may run)
+  float v_cap;           // speed bound of the tame domain for this archetype (tame_archetype)
   bool float_dma;        // te_step(TE_HOST) with float outputs: let the copy engine write the float arrays (no host expansion)
   cudaEvent_t ev_copy[64];
   ExpandPool *pool;
@@ -230,7 +232,38 @@ static void fill_idm(IdmConst &c, const float *a, float rate) {
   c.pow2 = is_pow2_f(a[7]) && is_pow2_f(rate) && !getenv("TE_NO_POW2_SHORTCUT");
 }
 
-static bool fast_arch(const te_handle *h) { return h->base.idm.pow2 && h->base.idm.delta_is_four; }
+// The FA kernels are compiled for the reference's archetype AND (TE_TAME_FAST) without the per-car validity predicate:
+// they may only run while the handle is tame.
+static bool fast_arch(const te_handle *h) { return h->base.idm.pow2 && h->base.idm.delta_is_four && h->tame; }
+
+// Archetype ranges under which tame car state stays tame and every fast sequence of idm_update is exact (te_math.cuh).
+// *v_cap = the speed bound of the tame domain for this archetype: twice the fastest speed the dynamics can produce
+// (v' <= max(v, v0 + a rate)), and at least the speed cars arrive with.  Closure needs the float dv = a (1 - p - q^2) to stay
+// finite (an infinite dv makes x NaN in the reference's arithmetic, and NaN state is not tame): q = s_star / (s + 1e-8)
+// is largest when the float gap s is -RN_f32(1e-8), where |s + 1e-8| = 6.08e-17, and s_star <= s0 + v T + v^2 / (2 sqrt(a b)).
+static bool tame_archetype(const te_config *cfg, float *v_cap) {
+  const float *a = cfg->archetype;
+  auto in = [](double v, double lo, double hi) { return std::isfinite(v) && v >= lo && v <= hi; };
+  const double tiny = ldexp(1.0, -10), big = ldexp(1.0, 19);
+  *v_cap = 0.f;
+  if (!(in(a[0], -ldexp(1.0, 30), ldexp(1.0, 30)) && (a[1] == 0.f || in(a[1], tiny, big)) && in(a[2], 0.0, big) &&
+        in(a[3], tiny, big) && in(a[4], tiny, 64.0) && in(a[5], tiny, big) && in(a[6], tiny, big) && in(a[7], tiny, big) &&
+        in(a[8], tiny, big) && in(cfg->rate, tiny, 1024.0) && in(cfg->length, tiny, ldexp(1.0, 30))))
+    return false;
+  const double cap = 2.0 * std::max((double)a[1], (double)a[5] + (double)a[3] * cfg->rate);
+  if (!(cap < big)) return false;
+  const double den_min = fabs((double)(float)1e-8 - 1e-8);
+  const double s_star_max = 1.01 * ((double)a[8] + cap * a[7] + cap * cap / (2.0 * sqrt((double)a[3] * a[6])));
+  const double q_max = s_star_max / den_min;
+  if (!((double)a[3] * (q_max * q_max + pow(cap / a[5], (double)a[4]) + 1.0) < ldexp(1.0, 126))) return false;
+  *v_cap = (float)cap;
+  return true;
+}
+static bool tame_car(float x, float v, float v_cap) {
+  return std::isfinite(x) && fabsf(x) < ldexpf(1.f, 40) && std::isfinite(v) &&
+         (v == 0.f ? !std::signbit(v) : (v >= ldexpf(1.f, -100) && v <= v_cap));
+}
+static int select_layout(te_handle *h);
 
 extern "C" const char *te_last_error(void) { return g_err.c_str(); }
 
@@ -312,6 +345,44 @@ extern "C" int te_destroy(te_handle *h) { free_handle(h); return 0; }
 
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
+
+// Threads per CTA, env instances per CTA and the kernel variant of a handle; called by te_create and again when a
+// handle stops being tame (te_set_state with a wild car: the checked, one-env-per-CTA kernels take over).
+static int select_layout(te_handle *h) {
+  const te_config *cfg = &h->cfg;
+  StepParams &p = h->base;
+#define CUH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+  // One thread per road.  Small grids put G env instances on one CTA (its rows are the G * R roads of those envs) so
+  // that no lane is a padding lane and a warp's car list is long: G in 1..4 with at most 256 rows, chosen for the
+  // fewest padding lanes (ties: the smaller G).  Default 3x3 grid: R = 48 -> G = 2, 96 threads, three warps.
+  // Large grids: G = 1, the CTA padded like the HBM rows (Rp).
+  if (h->Rp > 1024) { return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
+  const bool validate = (cfg->flags & TE_VALIDATE) != 0;
+  h->G = 1; h->threads = h->Rp;
+  if (!validate && h->R < 128 && fast_arch(h)) {
+    double best = (double)(h->Rp - h->R) / h->Rp;
+    for (int g = 2; g <= 4 && g * h->R <= 256; g++) {
+      const int th = (g * h->R + 31) / 32 * 32;
+      const double waste = (double)(th - g * h->R) / th;
+      if (waste < best - 1e-9) { best = waste; h->G = g; h->threads = th; }
+    }
+  }
+  if (const char *ev = getenv("TE_ENVS_PER_CTA")) {   // study knob
+    const int g = atoi(ev);
+    if (g >= 1 && g <= 8 && g * h->R <= 256 && !validate && fast_arch(h)) { h->G = g; h->threads = g == 1 ? h->Rp : (g * h->R + 31) / 32 * 32; }
+  }
+  h->warps = h->threads / GROUP_ROADS;
+  p.G = h->G;
+  CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const StepVariant sv = step_variant_for(h->threads, validate, fast_arch(h), h->G > 1);
+  if (h->threads > sv.maxt) { return fail("te_create: %d roads exceed the largest%s kernel variant (%d)", h->threads, validate ? " validate-mode" : "", sv.maxt); }
+  const int smem_max = smem_bytes(sv.maxt, validate, MAX_K, h->n_entry, h->G);
+  if (smem_max > h->smem_optin) { return fail("te_create: env needs %d B of shared memory, device allows %d", smem_max, h->smem_optin); }
+  CUH(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+
+#undef CUH
+  return 0;
+}
 
 extern "C" int te_create(const te_config *cfg, te_handle **out) {
   if (!cfg || !out) return fail("te_create: null argument");
@@ -487,6 +558,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.flags = cfg->flags; p.arrival_mode = cfg->arrival_mode; p.K = 1; p.raw = 0; p.episode_len = cfg->episode_len;
   p.gamma = cfg->gamma;
   fill_idm(p.idm, cfg->archetype, cfg->rate);
+  h->tame = tame_archetype(cfg, &h->v_cap);
   CUH(dalloc(&h->d_idm, 1));
   CUH(cudaMemcpy(h->d_idm, &p.idm, sizeof(IdmConst), cudaMemcpyHostToDevice));
   p.idm_g = h->d_idm;
@@ -498,33 +570,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0; p.sched_first = 0;
   p.nsteps = 1; p.controller = CTRL_GIVEN; p.actions_out = nullptr; p.env_mask = nullptr;
 
-  // One thread per road.  Small grids put G env instances on one CTA (its rows are the G * R roads of those envs) so
-  // that no lane is a padding lane and a warp's car list is long: G in 1..4 with at most 256 rows, chosen for the
-  // fewest padding lanes (ties: the smaller G).  Default 3x3 grid: R = 48 -> G = 2, 96 threads, three warps.
-  // Large grids: G = 1, the CTA padded like the HBM rows (Rp).
-  if (h->Rp > 1024) { free_handle(h); return fail("te_create: %d roads exceed one CTA (max 1024)", h->Rp); }
-  const bool validate = (cfg->flags & TE_VALIDATE) != 0;
-  h->G = 1; h->threads = h->Rp;
-  if (!validate && h->R < 128 && fast_arch(h)) {
-    double best = (double)(h->Rp - h->R) / h->Rp;
-    for (int g = 2; g <= 4 && g * h->R <= 256; g++) {
-      const int th = (g * h->R + 31) / 32 * 32;
-      const double waste = (double)(th - g * h->R) / th;
-      if (waste < best - 1e-9) { best = waste; h->G = g; h->threads = th; }
-    }
-  }
-  if (const char *ev = getenv("TE_ENVS_PER_CTA")) {   // study knob
-    const int g = atoi(ev);
-    if (g >= 1 && g <= 8 && g * h->R <= 256 && !validate && fast_arch(h)) { h->G = g; h->threads = g == 1 ? h->Rp : (g * h->R + 31) / 32 * 32; }
-  }
-  h->warps = h->threads / GROUP_ROADS;
-  p.G = h->G;
-  CUH(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  const StepVariant sv = step_variant_for(h->threads, validate, fast_arch(h), h->G > 1);
-  if (h->threads > sv.maxt) { free_handle(h); return fail("te_create: %d roads exceed the largest%s kernel variant (%d)", h->threads, validate ? " validate-mode" : "", sv.maxt); }
-  const int smem_max = smem_bytes(sv.maxt, validate, MAX_K, h->n_entry, h->G);
-  if (smem_max > h->smem_optin) { free_handle(h); return fail("te_create: env needs %d B of shared memory, device allows %d", smem_max, h->smem_optin); }
-  CUH(cudaFuncSetAttribute(sv.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  if (int rc = select_layout(h)) { free_handle(h); return rc; }
 
   // as-if-reset initial state with all-zero phases (the reference leaves state undefined before reset())
   te_reset_kernel<<<(cfg->num_envs + RESET_ENVS_PER_CTA - 1) / RESET_ENVS_PER_CTA, 128, 0, h->stream>>>(p, nullptr, nullptr, 0);
@@ -939,6 +985,7 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
   std::vector<uint8_t> hph((size_t)I * count), hpd((size_t)I * count);
   std::vector<EnvScalars> hes(count);
   CU(cudaMemcpy(hes.data(), h->env + env_begin, hes.size() * sizeof(EnvScalars), cudaMemcpyDeviceToHost));
+  bool wild = false;
   for (int e = 0; e < count; e++) {
     for (int rd = 0; rd < h->Rp; rd++) {
       uint32_t w0 = pack_meta(1, 1, 0); int wt = 0;
@@ -946,6 +993,16 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
       if (rd < R) {
         const int ld = leading[(size_t)e * R + rd], lc = lastcar[(size_t)e * R + rd];
         if (ld < 1 || ld >= CAP || lc < 1 || lc >= CAP) return fail("te_set_state: ring index out of range");
+        // every live car (and the leading slot's x, the virtual leader: finite or +inf) must be tame for the unchecked
+        // arithmetic; one wild car moves the whole handle to the checked kernels for good
+        for (int sl = ld; sl != lc;) {
+          sl = sl + 1 >= CAP ? 1 : sl + 1;
+          if (!tame_car(x[((size_t)e * R + rd) * CAP + sl], v[((size_t)e * R + rd) * CAP + sl], h->v_cap)) wild = true;
+        }
+        {
+          const float lx = x[((size_t)e * R + rd) * CAP + ld];
+          if (!(lx == INFINITY || (std::isfinite(lx) && fabsf(lx) < ldexpf(1.f, 40)))) wild = true;
+        }
         memcpy(xr, &x[((size_t)e * R + rd) * CAP], CAP * 4);
         memcpy(vr, &v[((size_t)e * R + rd) * CAP], CAP * 4);
         const int det = rd < r ? obs[(size_t)e * ol + r + rd] : 0;
@@ -973,6 +1030,17 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
   CU(cudaMemcpyAsync(h->env + env_begin, hes.data(), hes.size() * sizeof(EnvScalars), cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaDeviceSynchronize());
+  if (wild && h->tame) {      // from now on: the kernels with the per-car validity predicate, one env per CTA
+    h->tame = false;
+    if (int rc = select_layout(h)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int te_is_tame(const te_handle *h, int32_t *tame, float *v_cap) {
+  if (!h || !tame) return fail("te_is_tame: null argument");
+  *tame = h->tame ? 1 : 0;
+  if (v_cap) *v_cap = h->v_cap;
   return 0;
 }
 
@@ -1081,8 +1149,18 @@ extern "C" int te_test_powf(int device, const float *x, float y, float *out, int
   return 0;
 }
 
+static int test_idm(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
+                    const float *x, const float *v, float *x_out, float *v_out, int64_t n, int unchecked);
 extern "C" int te_test_idm(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
                            const float *x, const float *v, float *x_out, float *v_out, int64_t n) {
+  return test_idm(device, rate, a, xl, vl, ll, x, v, x_out, v_out, n, 0);
+}
+extern "C" int te_test_idm_tame(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
+                                const float *x, const float *v, float *x_out, float *v_out, int64_t n) {
+  return test_idm(device, rate, a, xl, vl, ll, x, v, x_out, v_out, n, 1);
+}
+static int test_idm(int device, float rate, const float *a, const float *xl, const float *vl, const float *ll,
+                    const float *x, const float *v, float *x_out, float *v_out, int64_t n, int unchecked) {
   CU(cudaSetDevice(device));
   CU(upload_math_consts());
   IdmConst c;
@@ -1094,7 +1172,7 @@ extern "C" int te_test_idm(int device, float rate, const float *a, const float *
   CU(cudaMemcpy(dc, &c, sizeof(IdmConst), cudaMemcpyHostToDevice));
   for (int i = 0; i < 7; i++) CU(cudaMalloc(&d[i], n * 4));
   for (int i = 0; i < 5; i++) CU(cudaMemcpy(d[i], src[i], n * 4, cudaMemcpyHostToDevice));
-  te_test_idm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(c, dc, d[0], d[1], d[2], d[3], d[4], d[5], d[6], n);
+  te_test_idm_kernel<<<(unsigned)((n + 255) / 256), 256>>>(c, dc, d[0], d[1], d[2], d[3], d[4], d[5], d[6], n, unchecked);
   CU(cudaGetLastError());
   CU(cudaMemcpy(x_out, d[5], n * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(v_out, d[6], n * 4, cudaMemcpyDeviceToHost));
@@ -1113,7 +1191,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
   // latency study: TE_PEAK_WARPS_PER_SM = w runs w warps per SM (one CTA of w warps per SM) instead
-  const int ilp2 = getenv("TE_PEAK_ILP2") ? 1 : 0;   // latency study: two independent cars per lane
+  const int ilp2 = getenv("TE_PEAK_ILP2") ? atoi(getenv("TE_PEAK_ILP2")) : 0;   // latency study: 1 = two idm_update calls per lane; 2 / 3 = split fast path, one / two cars
   if (const char *ev = getenv("TE_PEAK_WARPS_PER_SM")) { const int w = atoi(ev); if (w >= 1 && w <= 32) { threads = 32 * w; blocks = sms; } }
   float *sink = nullptr;
   CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
@@ -1130,7 +1208,7 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  *updates_per_sec = (double)threads * blocks * iters * (ilp2 ? 2 : 1) / (ms * 1e-3);
+  *updates_per_sec = (double)threads * blocks * iters * ((ilp2 == 1 || ilp2 == 3) ? 2 : 1) / (ms * 1e-3);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink); cudaFree(dc);
   return 0;
 }

@@ -310,6 +310,9 @@ __device__ __forceinline__ int transfer(const StepParams &p, const Smem &s, int 
 }
 
 constexpr int NO_OVERFLOW = 0x7fffffff;
+#ifndef TE_TAME_FAST
+#define TE_TAME_FAST 1   // the FA kernels run the unchecked arithmetic (te_math.cuh: CHECKED = false); te_api.cu only launches them on tame handles
+#endif
 #ifndef TE_UNIFORM_CAR_LOOP
 #define TE_UNIFORM_CAR_LOOP 1   // measured: the per-lane trip count (0) is 4.5 % / 8 % slower (10x10 / 3x3): lanes drifting apart cost more than the re-convergence
 #endif
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
           float xn = lds_f32(addr), vn = lds_f32_off<VOFF>(addr);
           const float xl = px, vl = pv, ll = pl;
           px = xn; pv = vn; pl = c.len;
-          idm_update<FA>(c, p.idm_g, s.tabs, xl, vl, ll, xn, vn);
+          idm_update<FA, !(FA && TE_TAME_FAST)>(c, p.idm_g, s.tabs, xl, vl, ll, xn, vn);
           sts_f32(addr, xn); sts_f32_off<VOFF>(addr, vn);
           // wrapped ring, low segment (slot < leading): the reference tests x, not v (traffic_env.py:210).
           // THRESH = 0.2 is compared in double by the reference; 0.2f is the smallest float above 0.2, so for every
@@ -1011,12 +1014,13 @@ __global__ void te_test_powf_kernel(const float *x, float y, float *out, long lo
   if (i < n) out[i] = powf_glibc(x[i], y, &g_powf_tables);
 }
 __global__ void te_test_idm_kernel(IdmConst c, const IdmConst *cg, const float *xl, const float *vl, const float *ll, const float *x,
-                                   const float *v, float *xo, float *vo, long long n) {
+                                   const float *v, float *xo, float *vo, long long n, int unchecked) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float xx = x[i], vv = v[i];
-    if (c.pow2 && c.delta_is_four) idm_update<true>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
-    else idm_update<false>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
+    if (unchecked) idm_update<true, false>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);   // tame operands only
+    else if (c.pow2 && c.delta_is_four) idm_update<true, true>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
+    else idm_update<false, true>(c, cg, &g_powf_tables, xl[i], vl[i], ll[i], xx, vv);
     xo[i] = xx; vo[i] = vv;
   }
 }
@@ -1031,19 +1035,46 @@ __global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, fl
   float x = 0.f, v = 5.f + 0.001f * (float)(gid & 1023);
   float xl = 30.f + 0.01f * (float)(gid & 255);
   const float vl = 9.f, step = __fmul_rn(vl, c.rate);
+  if (ilp2 == 4) {   // the production fast path with the archetype flags known at compile time (what the step kernel runs)
+    for (int i = 0; i < iters; i++) {
+      idm_update<true, true>(c, cg, &tabs, xl, vl, c.len, x, v);
+      xl = __fadd_rn(xl, step);
+    }
+    sink[gid] = x + v;
+    return;
+  }
+  if (ilp2 >= 2) {
+    // latency study: the split fast path (idm_study_part1 / part2), one car per lane (ilp2 == 2) or two cars whose first
+    // parts share a basic block (ilp2 == 3)
+    float x2 = 1.f, v2 = 6.f + 0.001f * (float)(gid & 511), xl2 = 40.f + 0.01f * (float)(gid & 127);
+    for (int i = 0; i < iters; i++) {
+      const IdmMid ma = idm_study_part1(c, xl, vl, c.len, x, v);
+      if (ilp2 == 3) {
+        const IdmMid mb = idm_study_part1(c, xl2, vl, c.len, x2, v2);
+        idm_study_part2(c, &tabs, ma, x, v);
+        idm_study_part2(c, &tabs, mb, x2, v2);
+        xl2 = __fadd_rn(xl2, step);
+      } else {
+        idm_study_part2(c, &tabs, ma, x, v);
+      }
+      xl = __fadd_rn(xl, step);
+    }
+    sink[gid] = x + v + x2 + v2;
+    return;
+  }
   if (ilp2) {
     // latency study: TWO independent cars per lane (one straight-line block: the compiler interleaves the chains)
     float x2 = 1.f, v2 = 6.f + 0.001f * (float)(gid & 511), xl2 = 40.f + 0.01f * (float)(gid & 127);
     for (int i = 0; i < iters; i++) {
-      idm_update<false>(c, cg, &tabs, xl, vl, c.len, x, v);
-      idm_update<false>(c, cg, &tabs, xl2, vl, c.len, x2, v2);
+      idm_update<false, true>(c, cg, &tabs, xl, vl, c.len, x, v);
+      idm_update<false, true>(c, cg, &tabs, xl2, vl, c.len, x2, v2);
       xl = __fadd_rn(xl, step); xl2 = __fadd_rn(xl2, step);
     }
     sink[gid] = x + v + x2 + v2;
     return;
   }
   for (int i = 0; i < iters; i++) {
-    idm_update<false>(c, cg, &tabs, xl, vl, c.len, x, v);
+    idm_update<false, true>(c, cg, &tabs, xl, vl, c.len, x, v);
     xl = __fadd_rn(xl, step);
   }
   sink[gid] = x + v;

@@ -392,6 +392,18 @@ class VecTrafficEnv(object):
             warnings.warn(self._L.te_last_error().decode("utf-8", "replace"))
         return envs, trips
 
+    def is_tame(self):
+        """True while the handle runs the kernels without the per-car validity predicate (te_is_tame)."""
+        t = C.c_int32(0)
+        check(self._L.te_is_tame(self._h, C.byref(t), None))
+        return bool(t.value)
+
+    def tame_speed_cap(self):
+        """Largest car speed te_set_state accepts without leaving the tame mode (0.0: archetype outside the ranges)."""
+        t, cap = C.c_int32(0), C.c_float(0)
+        check(self._L.te_is_tame(self._h, C.byref(t), C.byref(cap)))
+        return float(cap.value)
+
     def stats(self):
         s = _lib.TeStats()
         check(self._L.te_get_stats(self._h, C.byref(s)))
