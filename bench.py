@@ -728,10 +728,11 @@ def b200_arm(a):
 
     barrier(c)
     flush_gbs = env.stage_bandwidth(5) if c.rank == 0 else None
-    arith_peak = None
+    arith_peak = arith_peak_general = None
     if c.rank == 0:
         from traffic_env_b200.vec_env import idm_arithmetic_peak
-        arith_peak = idm_arithmetic_peak(device=c.local)
+        arith_peak = idm_arithmetic_peak(device=c.local)                     # the form the step kernels run (tame handle)
+        arith_peak_general = idm_arithmetic_peak(device=c.local, form=0)     # general checked form: round 1's denominator
     arith_peak = allreduce(c, [arith_peak or 0.0], "max")[0]
     run.close()
     secondary = None
@@ -760,9 +761,15 @@ def b200_arm(a):
             "roofline_flush": {"bound": "hbm", "achieved": flush_gbs, "peak": peak, "unit": "GB/s", "frac": flush_gbs / peak,
                                "what": "the step kernel's bulk-TMA stage-in + flush alone (te_stage_kernel: same CTA shape "
                                "and shared-memory footprint, no ticks), read + written bytes"},
-            "roofline_compute": {"bound": "idm arithmetic (registers only, all lanes busy: te_idm_peak micro-kernel)",
+            "roofline_compute": {"bound": "idm arithmetic (registers only, all lanes busy: te_idm_peak_form micro-kernel, the "
+                                 "form of the update the step kernel runs - compile-time archetype, no validity predicate - at "
+                                 "the better of 32 and 64 warps per SM)",
                                  "achieved": k_vu / (k_ms * 1e-3), "peak": arith_peak,
-                                 "unit": "vehicle-updates/s", "frac": k_vu / (k_ms * 1e-3) / arith_peak},
+                                 "unit": "vehicle-updates/s", "frac": k_vu / (k_ms * 1e-3) / arith_peak,
+                                 "peak_general_checked_form": arith_peak_general,
+                                 "frac_of_general_checked_form": k_vu / (k_ms * 1e-3) / arith_peak_general,
+                                 "note": "round 1 and the round-2 profiles before the tame mode quote fractions of the "
+                                 "general checked form's rate"},
             "roofline_issue": {"ops_per_vehicle_update": OPS_PER_UPDATE,
                                "achieved_gops": k_vu * OPS_PER_UPDATE / (k_ms * 1e-3) / 1e9,
                                "fp32_peak_gops_nominal_at_clock": fp32_peak / 1e9 if fp32_peak else None},

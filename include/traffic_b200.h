@@ -250,6 +250,12 @@ int te_stage_bandwidth(te_handle *h, int32_t repeats, double *gbytes_per_sec);
    occupied GPU does nothing but dependent IDM updates (traffic_env.py:50-62) in registers.  Used by bench.py
    as the compute roofline of the step kernel. */
 int te_idm_peak(int device, const float *archetype, float rate, int32_t iters, double *updates_per_sec);
+/* The same for one form of the update and one occupancy.  form: -1 = the form the step kernels run for this archetype on
+   a tame handle, 0 = general checked form (te_idm_peak), 4 = compile-time archetype flags + validity predicate, 5 = the
+   same without the predicate (tame handles), 1..3 = latency studies (two calls per lane; split fast path with one / two
+   cars per lane).  warps_per_sm: 0 = 2048 resident threads per SM, else one CTA of that many warps per SM (1..32). */
+int te_idm_peak_form(int device, const float *archetype, float rate, int32_t iters, int32_t form, int32_t warps_per_sm,
+                     double *updates_per_sec);
 
 /* ---- test hooks (host pointers): device arithmetic exposed for bit-exactness tests */
 /* out[i] = device restatement of glibc powf(x[i], y) (numba lowers float32 ** to libm powf). */

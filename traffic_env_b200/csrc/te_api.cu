@@ -1181,18 +1181,26 @@ static int test_idm(int device, float rate, const float *a, const float *xl, con
   return 0;
 }
 
-extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters, double *updates_per_sec) {
-  if (!a || !updates_per_sec || iters < 1) return fail("te_idm_peak: bad argument");
+extern "C" int te_idm_peak_form(int device, const float *a, float rate, int32_t iters, int32_t form, int32_t warps_per_sm,
+                                double *updates_per_sec) {
+  if (!a || !updates_per_sec || iters < 1 || form < -1 || form > 5 || warps_per_sm < 0 || warps_per_sm > 32)
+    return fail("te_idm_peak_form: bad argument");
   CU(cudaSetDevice(device));
   CU(upload_math_consts());
   IdmConst c;
   fill_idm(c, a, rate);
+  if (form < 0) {   // the form the step kernels run for this archetype
+    te_config cfg; te_default_config(&cfg);
+    memcpy(cfg.archetype, a, sizeof(cfg.archetype)); cfg.rate = rate;
+    float cap;
+    const bool fa = c.pow2 && c.delta_is_four;
+    form = fa ? (tame_archetype(&cfg, &cap) ? 5 : 4) : 0;
+  }
+  if (form >= 1 && !(c.pow2 && c.delta_is_four)) return fail("te_idm_peak_form: forms 1..5 need the power-of-two archetype");
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  int threads = 256, blocks = sms * 8;  // 2048 resident threads per SM
-  // latency study: TE_PEAK_WARPS_PER_SM = w runs w warps per SM (one CTA of w warps per SM) instead
-  const int ilp2 = getenv("TE_PEAK_ILP2") ? atoi(getenv("TE_PEAK_ILP2")) : 0;   // latency study: 1 = two idm_update calls per lane; 2 / 3 = split fast path, one / two cars
-  if (const char *ev = getenv("TE_PEAK_WARPS_PER_SM")) { const int w = atoi(ev); if (w >= 1 && w <= 32) { threads = 32 * w; blocks = sms; } }
+  int threads = 256, blocks = sms * 8;  // warps_per_sm == 0: 2048 resident threads per SM
+  if (warps_per_sm) { threads = 32 * warps_per_sm; blocks = sms; }   // one CTA of w warps per SM
   float *sink = nullptr;
   CU(cudaMalloc(&sink, (size_t)threads * blocks * 4));
   IdmConst *dc = nullptr;
@@ -1200,17 +1208,21 @@ extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters
   CU(cudaMemcpy(dc, &c, sizeof(IdmConst), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters / 4 + 1, sink, ilp2);  // warm-up
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters / 4 + 1, sink, form);  // warm-up
   CU(cudaEventRecord(e0));
-  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters, sink, ilp2);
+  te_idm_peak_kernel<<<blocks, threads>>>(c, dc, iters, sink, form);
   CU(cudaEventRecord(e1));
   CU(cudaEventSynchronize(e1));
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  *updates_per_sec = (double)threads * blocks * iters * ((ilp2 == 1 || ilp2 == 3) ? 2 : 1) / (ms * 1e-3);
+  *updates_per_sec = (double)threads * blocks * iters * ((form == 1 || form == 3) ? 2 : 1) / (ms * 1e-3);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink); cudaFree(dc);
   return 0;
+}
+
+extern "C" int te_idm_peak(int device, const float *a, float rate, int32_t iters, double *updates_per_sec) {
+  return te_idm_peak_form(device, a, rate, iters, 0, 0, updates_per_sec);
 }
 
 extern "C" int te_test_powf4_exhaustive(int device, uint64_t tau, uint64_t out[4]) {

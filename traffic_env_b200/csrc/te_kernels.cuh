@@ -1035,7 +1035,15 @@ __global__ void te_idm_peak_kernel(IdmConst c, const IdmConst *cg, int iters, fl
   float x = 0.f, v = 5.f + 0.001f * (float)(gid & 1023);
   float xl = 30.f + 0.01f * (float)(gid & 255);
   const float vl = 9.f, step = __fmul_rn(vl, c.rate);
-  if (ilp2 == 4) {   // the production fast path with the archetype flags known at compile time (what the step kernel runs)
+  if (ilp2 == 5) {   // what the step kernels run on a tame handle: archetype flags known at compile time, no validity predicate
+    for (int i = 0; i < iters; i++) {
+      idm_update<true, false>(c, cg, &tabs, xl, vl, c.len, x, v);
+      xl = __fadd_rn(xl, step);
+    }
+    sink[gid] = x + v;
+    return;
+  }
+  if (ilp2 == 4) {   // the same with the validity predicate and the generic fallback (a handle that saw a wild car)
     for (int i = 0; i < iters; i++) {
       idm_update<true, true>(c, cg, &tabs, xl, vl, c.len, x, v);
       xl = __fadd_rn(xl, step);

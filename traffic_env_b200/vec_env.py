@@ -424,10 +424,15 @@ class VecTrafficEnv(object):
         check(self._L.te_synchronize(self._h))
 
 
-def idm_arithmetic_peak(device=0, rate=0.5, archetype=None, iters=4000):
-    """vehicle-updates/s of the IDM arithmetic alone on a fully occupied GPU (te_idm_peak)."""
+def idm_arithmetic_peak(device=0, rate=0.5, archetype=None, iters=4000, form=-1, warps_per_sm=None):
+    """vehicle-updates/s of the IDM arithmetic alone, registers only, every lane busy (te_idm_peak_form).  form -1: the
+    form the step kernels run for this archetype on a tame handle; 0: the general checked form (the denominator of the
+    round-1 figures).  warps_per_sm None: the better of 32 warps per SM (the step kernels' occupancy) and 64."""
     L = _lib.load()
     arch = np.ascontiguousarray(ARCHETYPE if archetype is None else archetype, dtype=np.float32)
-    out = C.c_double()
-    check(L.te_idm_peak(int(device), arch.ctypes.data, float(rate), int(iters), C.byref(out)))
-    return out.value
+    best = 0.0
+    for w in ((32, 0) if warps_per_sm is None else (int(warps_per_sm),)):
+        out = C.c_double()
+        check(L.te_idm_peak_form(int(device), arch.ctypes.data, float(rate), int(iters), int(form), w, C.byref(out)))
+        best = max(best, out.value)
+    return best
