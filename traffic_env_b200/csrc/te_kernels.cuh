@@ -140,8 +140,15 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 // compile-time function of the kernel variant's row capacity MAXT (>= G * R rounded up to whole warps) so that the tick
 // loop addresses shared memory with immediates; only the tail has a run-time size: per env the arrival-count table
 // (K * n_entry bytes), the Philox (draw, skip) snapshots before each tick and two per-env tick stamps.
+enum : int { ENVM_OVF = 0,    // first overflowing tick of the current actor step (NO_OVERFLOW: none yet)
+             ENVM_ORD = 1,    // last tick of the launch (CTA-wide count) that needs ordered transfers
+             ENVM_TB = 2,     // ticks this env ran in the earlier actor steps of this launch
+             ENVM_SKIP = 3,   // env not stepped (env_mask)
+             ENVM_WORDS = 4 };
+constexpr int MAX_G = 8;           // most env instances one CTA can hold (te_api.cu: select_layout)
+
 struct SmemLayout {
-  int xs, vs, ws, tabs, mbar, tailx, meta, wait, elapsed, ovf, rew, misc, warp, phase, act, pdst, cnt;
+  int xs, vs, ws, tabs, mbar, tailx, meta, wait, elapsed, ovf, rew, misc, envm, warp, phase, act, pdst, cnt;
 };
 
 __host__ __device__ constexpr int align_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -162,6 +169,7 @@ __host__ __device__ constexpr SmemLayout make_layout(int maxt, bool validate) {
   L.ovf = o; o += icap * 4;
   L.rew = o; o += icap * 4;
   L.misc = o; o += 32;
+  L.envm = o; o += MAX_G * ENVM_WORDS * 4;                // per-env words (ENVM_*): a fixed place, so the tick loop reaches them with immediates
   o = align_up(o, 16);
   L.warp = o; o += (maxt / GROUP_ROADS) * WARP_AREA;
   L.phase = o; o += icap;
@@ -178,17 +186,12 @@ static_assert(make_layout(64, false).warp % 16 == 0 && make_layout(512, false).w
               make_layout(512, false).vs % 16 == 0 && make_layout(512, true).ws % 16 == 0 && make_layout(64, false).cnt % 16 == 0,
               "shared-memory layout alignment");
 // run-time tail, KT = ticks of the whole launch (nsteps * K):
-//   [G][cnt_stride] arrival counts | [G][KT + 1][2] Philox snapshots | [G][4] per-env words (ENVM_*)
+//   [G][cnt_stride] arrival counts | [G][KT + 1][2] Philox snapshots
 __host__ __device__ constexpr int cnt_stride_bytes(int KT, int n_entry) { return align_up(KT * (n_entry > 0 ? n_entry : 1), 4); }
 __host__ __device__ constexpr int tail_snap_offset(int KT, int n_entry, int G) { return align_up(G * cnt_stride_bytes(KT, n_entry), 8); }
 __host__ __device__ constexpr int smem_bytes(int maxt, bool validate, int KT, int n_entry, int G) {
-  return make_layout(maxt, validate).cnt + align_up(tail_snap_offset(KT, n_entry, G) + G * (KT + 1) * 8 + G * 16, 16);
+  return make_layout(maxt, validate).cnt + align_up(tail_snap_offset(KT, n_entry, G) + G * (KT + 1) * 8, 16);
 }
-enum : int { ENVM_OVF = 0,    // first overflowing tick of the current actor step (NO_OVERFLOW: none yet)
-             ENVM_ORD = 1,    // last tick of the launch (CTA-wide count) that needs ordered transfers
-             ENVM_TB = 2,     // ticks this env ran in the earlier actor steps of this launch
-             ENVM_SKIP = 3,   // env not stepped (env_mask)
-             ENVM_WORDS = 4 };
 
 // ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier: the env's ring planes are contiguous in HBM, so
 // one elected thread moves each plane with a single instruction while the other threads set up the tick loop.
@@ -245,6 +248,29 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+template <int OFF>
+__device__ __forceinline__ void sts_u32_off(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32_off(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_u16_off(uint32_t a, unsigned short v) {
+  asm volatile("st.shared.u16 [%0+%1], %2;" ::"r"(a), "n"(OFF), "h"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ int lds_u16_off(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF) : "memory");
+  return (int)v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void red_add_shared(uint32_t a, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -273,6 +299,7 @@ struct Smem {
   int *wait, *elapsed, *ovf;
   float *rew;            // reward of the finished actor step per intersection (for the return statistic)
   unsigned long long *mbar;
+  int *envm;             // per env of the CTA: ENVM_WORDS words (tick stamps, ticks run, skip flag)
   int *misc;             // CTA level: [0] envs still running, [1] last tick in which some env needed ordered transfers, [2] vehicle updates, [3] overflows, [4] generated, [5] ordered-transfer env-ticks, [6] cars that left the map
   uint8_t *warp, *phase, *act, *pdst, *cnt;
   const PowfTables *tabs;  // glibc powf tables (global memory, L1-resident: read by ~0.4 % of the cars)
@@ -284,7 +311,7 @@ __device__ __forceinline__ Smem carve(unsigned char *base, const SmemLayout &L) 
   s.tailx = (float *)(base + L.tailx); s.mbar = (unsigned long long *)(base + L.mbar);
   s.meta = (uint32_t *)(base + L.meta); s.wait = (int *)(base + L.wait);
   s.elapsed = (int *)(base + L.elapsed); s.ovf = (int *)(base + L.ovf); s.rew = (float *)(base + L.rew);
-  s.misc = (int *)(base + L.misc); s.warp = base + L.warp; s.phase = base + L.phase; s.act = base + L.act;
+  s.misc = (int *)(base + L.misc); s.envm = (int *)(base + L.envm); s.warp = base + L.warp; s.phase = base + L.phase; s.act = base + L.act;
   s.pdst = base + L.pdst; s.cnt = base + L.cnt; s.tabs = &g_powf_tables;
   return s;
 }
@@ -342,7 +369,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   // run-time tail of the shared-memory layout (per env: arrival counts, Philox snapshots, ENVM words)
   const int cnt_stride = cnt_stride_bytes(KT, p.n_entry);
   uint32_t *const snap_base = reinterpret_cast<uint32_t *>(s.cnt + tail_snap_offset(KT, p.n_entry, G));
-  int *const envm = reinterpret_cast<int *>(snap_base + G * 2 * (KT + 1));
+  int *const envm = s.envm;
   const int nrows = ng * p.R;                                // live rows (super-roads) of this CTA
   const int nI = ng * p.I;
   const size_t ibase = (size_t)env_first * p.I;              // the per-intersection arrays of consecutive envs are contiguous
@@ -534,11 +561,12 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     ylim = (ls_act || road_phase == (int)s.phase[dst]) ? 0x7fffffff : YELLOW_TICKS - el0;
   }
   // per-warp tables of the car loop (rebuilt every tick)
-  uint4 *rt = reinterpret_cast<uint4 *>(s.warp + warp * WARP_AREA);      // non-empty roads of the warp, in lane order:
+  // (all three are reached from ONE 32-bit shared address, rt_a, with immediates: no generic pointers kept per table)
+  const uint32_t rt_a = smem_u32(s.warp + warp * WARP_AREA);             // rt: non-empty roads of the warp, in lane order:
                                                                          // shared addresses of x[leading], x[lastcar], x[19]; leader x
-  unsigned int *wcnt = reinterpret_cast<unsigned int *>(rt + 32);        // waiting | detected << 16 per listed road
-  unsigned short *wst = reinterpret_cast<unsigned short *>(wcnt + 32);   // first list position of each listed road
-  const uint32_t rt_a = smem_u32(rt), wcnt_a = smem_u32(wcnt);
+  constexpr int WCNT_OFF = 32 * 16;                                      // wcnt: waiting | detected << 16 per listed road
+  constexpr int WST_OFF = WCNT_OFF + 32 * 4;                             // wst: first list position of each listed road (u16)
+  const uint32_t wcnt_a = rt_a + WCNT_OFF;
   const uint32_t xrow_a = smem_u32(xr);                                  // shared address of x[my row][0]
   constexpr int VOFF = L.vs - L.xs;                                      // v plane relative to the x plane
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -589,10 +617,10 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     const unsigned mne = __ballot_sync(FULL, n > 0);
     const int nroads = __popc(mne);
     const int cidx = n > 0 ? __popc(mne & lt_mask) : nroads + __popc(~mne & lt_mask);
-    wst[cidx] = n > 0 ? (unsigned short)start : (unsigned short)0xffff;
+    sts_u16_off<WST_OFF>(rt_a + 2u * cidx, n > 0 ? (unsigned short)start : (unsigned short)0xffff);
     if (n > 0) {
-      rt[cidx] = make_uint4(xrow_a + 4u * ld, xrow_a + 4u * lc, xrow_a + 4u * RING, __float_as_uint(leadx));
-      wcnt[cidx] = 0u;
+      sts_v4(rt_a + 16u * cidx, make_uint4(xrow_a + 4u * ld, xrow_a + 4u * lc, xrow_a + 4u * RING, __float_as_uint(leadx)));
+      sts_u32_off<WCNT_OFF>(rt_a + 4u * cidx, 0u);
     }
     __syncwarp();
     if (total > 0) {
@@ -606,10 +634,10 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
       if (cnt > 0) {
         int lo = 0;
 #pragma unroll
-        for (int st = 16; st > 0; st >>= 1) if ((int)wst[lo + st] <= target) lo += st;
-        const int k = target - (int)wst[lo];                   // my first car is the k-th from the front of road `lo`
+        for (int st = 16; st > 0; st >>= 1) if (lds_u16_off<WST_OFF>(rt_a + 2u * (lo + st)) <= target) lo += st;
+        const int k = target - lds_u16_off<WST_OFF>(rt_a + 2u * lo);   // my first car is the k-th from the front of road `lo`
         jaddr = rt_a + 16u * lo; caddr = wcnt_a + 4u * lo;
-        const uint4 e = rt[lo];
+        const uint4 e = lds_v4(rt_a + 16u * lo);
         ldaddr = e.x; lcaddr = e.y; endaddr = e.z; px = __uint_as_float(e.w);
         addr = ldaddr + 4u * (k + 1);
         if (addr > endaddr) addr -= 4u * RING;                 // ring position ((leading + k) mod 19) + 1
@@ -659,7 +687,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (n > 0) {
       veh_local += n;
       if (is_train) {
-        const unsigned int cw = wcnt[cidx];
+        const unsigned int cw = lds_u32_off<WCNT_OFF>(rt_a + 4u * cidx);
         wait += (int)(cw & 0xffffu); det = (int)(cw >> 16);  // detected is only rewritten for non-empty roads (:194)
       }
       // advance_finished_cars, traffic_env.py:123: pop while the front car is past the end of the road
