@@ -153,6 +153,12 @@ int te_step_masked(te_handle *h, const uint8_t *actions, const uint8_t *env_mask
 enum te_controller { TE_CTRL_GIVEN = 0, TE_CTRL_GREEDY = 1 };
 int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks, float *obs,
                   float *reward, uint8_t *done, int memspace, void *stream);
+/* TE_CTRL_GREEDY launches of this handle take a new decision every `spacing` actor steps (greedy.py's --spacing: steps
+   0, spacing, 2 spacing ... of the launch), so one launch can hold several decisions: a whole device-resident rollout
+   segment of n_steps * k_ticks <= 64 ticks without the state leaving shared memory.  `actions` then receives
+   uint8[ceil(n_steps / spacing)][E, I], one block per decision.  Results are those of ceil(n_steps / spacing) launches
+   of `spacing` steps each.  0 (the default): one decision per launch. */
+int te_set_controller_spacing(te_handle *h, int32_t spacing);
 
 /* Env-slot pool for learner threads (a3c.py:66-72: FLAGS.threads workers, each stepping its own env): te_pool_step
    queues slot `slot`'s action (uint8[I]) and blocks until that slot has been advanced by one actor step of k_ticks ticks;

@@ -461,3 +461,77 @@ def test_wild_car_moves_the_handle_to_the_checked_kernels(m, n, L, E):
                 assert gx.tobytes() == ox.tobytes() and gv.tobytes() == ov.tobytes(), tag + " car state"
     # a tame state afterwards does not bring the unchecked kernels back (cars given earlier may still be on the roads)
     assert not env.is_tame()
+
+
+@pytest.mark.parametrize("m,n,L,E,lcps,extra", [
+    (3, 3, 250.0, 301, 0.5, {}), (10, 10, 500.0, 6, 0.3, {}), (2, 2, 120.0, 77, 0.9, {}), (4, 4, 150.0, 33, 0.4, {}),
+    (3, 3, 250.0, 65, 0.5, {"learn_switch": True}), (3, 3, 250.0, 40, 0.15, {"validate": True}), (3, 3, 250.0, 50, 0.5, {"remi": False}),
+    (3, 3, 250.0, 64, 0.12, {"ticks_per_step": 4})])
+def test_controller_decisions_inside_a_launch(m, n, L, E, lcps, extra):
+    """te_set_controller_spacing: one te_step_multi launch that holds several greedy decisions (a new one every
+    `spacing` actor steps, evaluated in the kernel on the live rings) produces exactly what one launch per decision
+    produces - actions of every decision, every actor step's obs / reward / done, host buffers, device buffers and wire
+    records, final car state and counters - including overflow steps (early break: the envs of a CTA then decide at
+    different ticks of the launch), learn_switch (the light toggles from the decision tick on), validate mode, a spacing
+    that does not divide the launch, and going back to one decision per launch on the same handle."""
+    import torch
+    from traffic_env_b200 import VecTrafficEnv
+    kw = dict(m=m, n=n, length=L, num_envs=E, arrivals="philox", seed=23, local_cars_per_sec=lcps, ticks_per_step=10, remi=True)
+    kw.update(extra)
+    K = kw["ticks_per_step"]
+    a, b, d, w = (VecTrafficEnv(**kw) for _ in range(4))
+    I = m * n
+    init = np.random.RandomState(5).randint(2, size=(E, I))
+    for env in (a, b, d, w):
+        env.reset(init_phase=init)
+    dev = torch.device("cuda", 0)
+    NMAX = 64 // K
+    d_act = torch.zeros((NMAX, E, I), dtype=torch.uint8, device=dev)
+    d_obs = torch.zeros((NMAX, E, a.obs_len), dtype=torch.float32, device=dev)
+    d_rew = torch.zeros((NMAX, E, I), dtype=torch.float32, device=dev)
+    d_done = torch.zeros((NMAX, E), dtype=torch.uint8, device=dev)
+    saw_done = 0
+    plans = [(6, 3), (6, 2), (5, 3), (6, 1), (4, 3), (3, None), (6, 3), (2, 5), (6, 4)] if K == 10 else [(16, 3), (12, 5), (16, 4), (9, None)]
+    for rep in range(3 if not extra.get("validate") else 4):
+        for ns, sp in plans:
+            ns = min(ns, NMAX)
+            act_b, obs_b, rew_b, done_b = b.step_multi(ns, controller="greedy", spacing=sp)
+            d.step_multi_device(ns, d_act, d_obs, d_rew, d_done, controller="greedy", spacing=sp)
+            act_w, rec = w.step_multi_wire(ns, controller="greedy", spacing=sp)
+            d.synchronize()
+            seg = ns if sp is None else sp
+            ndec = (ns + seg - 1) // seg
+            act_b = act_b.reshape(ndec, E, I)
+            act_w = act_w.reshape(ndec, E, I)
+            j = 0
+            for dec in range(ndec):
+                cnt = min(seg, ns - j)
+                act_a, obs_a, rew_a, done_a = a.step_multi(cnt, controller="greedy")       # one launch per decision
+                tag = (rep, ns, sp, dec)
+                assert act_a.tobytes() == act_b[dec].tobytes() == act_w[dec].tobytes(), tag
+                assert act_a.tobytes() == d_act[dec].cpu().numpy().tobytes(), tag
+                for q in range(cnt):
+                    assert obs_a[q].tobytes() == obs_b[j].tobytes() and rew_a[q].tobytes() == rew_b[j].tobytes() \
+                        and done_a[q].tobytes() == done_b[j].tobytes(), tag + (q,)
+                    assert obs_a[q].tobytes() == d_obs[j].cpu().numpy().tobytes() and rew_a[q].tobytes() == d_rew[j].cpu().numpy().tobytes() \
+                        and done_a[q].tobytes() == d_done[j].cpu().numpy().tobytes(), tag + (q,)
+                    assert rec["reward"][j].tobytes() == rew_a[q].tobytes() and (rec["done"][j] == done_a[q]).all(), tag + (q,)
+                    assert rec["light"][j].tobytes() == np.ascontiguousarray(obs_a[q][:, 2 * a.train_roads:]).tobytes(), tag + (q,)
+                    saw_done += int(done_a[q].sum())
+                    j += 1
+    sa = a.get_state()
+    for other in (b, d, w):
+        so = other.get_state()
+        for k in ("leading", "lastcar", "obs", "waiting", "passed_dst", "steps"):
+            assert (sa[k] == so[k]).all(), k
+        for e in range(E):
+            xa, va = live_walk(sa["leading"][e], sa["lastcar"][e], sa["x"][e], sa["v"][e])
+            xo, vo = live_walk(so["leading"][e], so["lastcar"][e], so["x"][e], so["v"][e])
+            assert xa.tobytes() == xo.tobytes() and va.tobytes() == vo.tobytes(), e
+        sta, sto = a.stats(), other.stats()
+        for k in ("ticks", "actor_steps", "vehicle_updates", "overflows", "cars_generated", "cars_exited"):
+            assert sta[k] == sto[k], k
+    assert saw_done > 0 or extra.get("validate") or K != 10, "the test is meant to include overflow steps"
+    if extra.get("validate"):
+        (ea, ta), (eb, tb) = a.trip_times(), b.trip_times()
+        assert len(ta) > 0 and ea.tobytes() == eb.tobytes() and ta.tobytes() == tb.tobytes()

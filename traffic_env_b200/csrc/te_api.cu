@@ -157,6 +157,8 @@ struct te_handle {
   int wire_stride, host_slices, wire_steps, float_steps;
   bool tame;             // every car the device has seen is tame (te_math.cuh: CHECKED = false may run)
   float v_cap;           // speed bound of the tame domain for this archetype (tame_archetype)
+  int ctrl_spacing;      // TE_CTRL_GREEDY: a new decision every so many actor steps inside a te_step_multi launch (0: one per launch)
+  int actions_cap;       // decisions d_actions has room for
   bool float_dma;        // te_step(TE_HOST) with float outputs: let the copy engine write the float arrays (no host expansion)
   cudaEvent_t ev_copy[64];
   ExpandPool *pool;
@@ -486,6 +488,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   CUH(dalloc(&h->d_nexts, (size_t)h->Rp)); CUH(dalloc(&h->d_up, (size_t)h->Rp));
   CUH(dalloc(&h->d_entry_idx, (size_t)h->Rp));
   CUH(dalloc(&h->d_actions, E * h->I)); CUH(dalloc(&h->d_done, E)); CUH(dalloc(&h->d_mask, E));
+  h->actions_cap = 1; h->ctrl_spacing = 0;
   CUH(dalloc(&h->d_init_phase, E * h->I));
   CUH(dalloc(&h->d_obs_i, E * (2 * h->r + 2 * h->I)));
   CUH(dalloc(&h->d_reward, E * h->I));
@@ -568,7 +571,7 @@ extern "C" int te_create(const te_config *cfg, te_handle **out) {
   p.gap_cdf = h->d_gap_cdf; p.n_gap = (int)cdf.size();
   p.seed = (uint32_t)(cfg->seed ^ (cfg->seed >> 32)); p.env_id_base = cfg->env_id_base;
   p.sched_off = nullptr; p.sched_roads = nullptr; p.horizon = 0; p.sched_first = 0;
-  p.nsteps = 1; p.controller = CTRL_GIVEN; p.actions_out = nullptr; p.env_mask = nullptr;
+  p.nsteps = 1; p.controller = CTRL_GIVEN; p.actions_out = nullptr; p.env_mask = nullptr; p.decide_every = 0;
 
   if (int rc = select_layout(h)) { free_handle(h); return rc; }
 
@@ -717,6 +720,16 @@ static int ensure_float_steps(te_handle *h, int nsteps) {
   return 0;
 }
 
+// room for the decisions of one launch in the device-side action buffer (host path)
+static int ensure_actions(te_handle *h, int ndec) {
+  if (ndec <= h->actions_cap) return 0;
+  CU(cudaDeviceSynchronize());
+  cudaFree(h->d_actions); h->d_actions = nullptr; h->actions_cap = 0;
+  CU(dalloc(&h->d_actions, (size_t)ndec * h->cfg.num_envs * h->I));
+  h->actions_cap = ndec;
+  return 0;
+}
+
 static int launch_step(te_handle *h, const StepReq &q) {
   const int K = q.K, raw = q.raw, nsteps = q.nsteps;
   const bool greedy = q.controller == CTRL_GREEDY;
@@ -734,7 +747,10 @@ static int launch_step(te_handle *h, const StepReq &q) {
   const bool use_wire = !raw && K <= WIRE_MAX_K && (q.wire_only || (host && (!h->float_dma || q.env_mask)));
   StepParams p = h->base;
   p.K = K; p.raw = raw; p.nsteps = nsteps; p.controller = q.controller; p.actions_out = nullptr; p.env_mask = q.env_mask;
+  p.decide_every = greedy ? h->ctrl_spacing : 0;
+  const int ndec = p.decide_every > 0 ? (nsteps + p.decide_every - 1) / p.decide_every : 1;   // controller decisions of this launch
   if (host) {
+    if (int rc = ensure_actions(h, ndec)) return rc;
     if (!greedy) CU(cudaMemcpyAsync(h->d_actions, q.actions, E * h->I, cudaMemcpyHostToDevice, st));
     if (q.env_mask) { CU(cudaMemcpyAsync(h->d_mask, q.env_mask, E, cudaMemcpyHostToDevice, st)); p.env_mask = h->d_mask; }
     p.actions = h->d_actions; p.actions_out = greedy ? h->d_actions : nullptr;
@@ -809,8 +825,8 @@ static int launch_step(te_handle *h, const StepReq &q) {
     }
     nk = k + 1;
   }
-  if (greedy && q.actions)   // the controller's choice, for the caller
-    CU(cudaMemcpyAsync(const_cast<uint8_t *>(q.actions), h->d_actions, E * h->I, cudaMemcpyDeviceToHost, h->stream_copy));
+  if (greedy && q.actions)   // the controller's choices, for the caller
+    CU(cudaMemcpyAsync(const_cast<uint8_t *>(q.actions), h->d_actions, (size_t)ndec * E * h->I, cudaMemcpyDeviceToHost, h->stream_copy));
   CU(cudaEventRecord(h->ev_join, h->stream2));
   CU(cudaEventRecord(h->ev_copied, h->stream_copy));
   CU(cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -848,6 +864,13 @@ extern "C" int te_step_multi(te_handle *h, int32_t n_steps, int32_t controller, 
   StepReq q; q.actions = actions; q.K = k_ticks; q.nsteps = n_steps; q.controller = controller == TE_CTRL_GREEDY ? CTRL_GREEDY : CTRL_GIVEN;
   q.obs = obs; q.reward = reward; q.done = done; q.memspace = memspace; q.stream = stream; q.who = "te_step_multi";
   return launch_step(h, q);
+}
+
+extern "C" int te_set_controller_spacing(te_handle *h, int32_t spacing) {
+  if (!h) return fail("te_set_controller_spacing: null handle");
+  if (spacing < 0 || spacing > MAX_K) return fail("te_set_controller_spacing: spacing must be in [0, %d]", MAX_K);
+  h->ctrl_spacing = spacing;
+  return 0;
 }
 
 extern "C" int te_step_multi_wire(te_handle *h, int32_t n_steps, int32_t controller, uint8_t *actions, int32_t k_ticks,

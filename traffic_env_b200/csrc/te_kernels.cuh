@@ -110,7 +110,8 @@ struct StepParams {
   // of actor step j go to obs / reward / done / wire + j * (their size for num_envs envs)
   int nsteps;
   int controller;               // CTRL_GIVEN: `actions` is read; CTRL_GREEDY: computed in the kernel from the ring counts
-  uint8_t *actions_out;         // CTRL_GREEDY: the actions chosen, [E][I] (nullable)
+  uint8_t *actions_out;         // CTRL_GREEDY: the actions chosen, [decisions][E][I] (nullable)
+  int decide_every;             // CTRL_GREEDY: a new decision every so many actor steps of the launch (0: one per launch)
   const uint8_t *env_mask;      // nullable; [E], zero = this env is not stepped (te_step_masked)
   // arrivals
   const long long *sched_off;   // [E*(horizon+1)]
@@ -144,7 +145,8 @@ enum : int { ENVM_OVF = 0,    // first overflowing tick of the current actor ste
              ENVM_ORD = 1,    // last tick of the launch (CTA-wide count) that needs ordered transfers
              ENVM_TB = 2,     // ticks this env ran in the earlier actor steps of this launch
              ENVM_SKIP = 3,   // env not stepped (env_mask)
-             ENVM_WORDS = 4 };
+             ENVM_SEG = 4,    // tick of the launch (for this env) at which the current controller decision was applied
+             ENVM_WORDS = 5 };
 constexpr int MAX_G = 8;           // most env instances one CTA can hold (te_api.cu: select_layout)
 
 struct SmemLayout {
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   if (tid == 0) { s.misc[0] = nactive; s.misc[1] = -1; s.misc[2] = 0; s.misc[3] = 0; s.misc[4] = 0; s.misc[5] = 0; s.misc[6] = 0; }
   if (tid < G) {
     envm[ENVM_WORDS * tid + ENVM_OVF] = NO_OVERFLOW; envm[ENVM_WORDS * tid + ENVM_ORD] = -1; envm[ENVM_WORDS * tid + ENVM_TB] = 0;
+    envm[ENVM_WORDS * tid + ENVM_SEG] = 0;
     envm[ENVM_WORDS * tid + ENVM_SKIP] = (tid >= ng) || (p.env_mask && p.env_mask[env_first + tid] == 0);
   }
   for (int g = warp; g < ng; g += nwarps) {
@@ -585,6 +588,43 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
   // A lane takes part in a tick while its env is still running: an env whose ring overflowed in tick t stops after t
   // (Repeater: `if done: break`, traffic_test.py:55) while the other envs of the CTA carry on; padding rows never run.
   // (One env per CTA: never frozen - padding rows are empty rings with no topology, and the loop simply ends.)
+  if (p.controller == CTRL_GREEDY && p.decide_every > 0 && step > 0 && step % p.decide_every == 0) {   // (CTA-uniform)
+    // A new controller decision inside the launch (greedy.py:13-17 decides every `--spacing` actor steps): what the
+    // prologue does from the staged state, on the live state.  Road lanes publish their ring indices; thread i < nI
+    // takes intersection i's light state after the last tick its env ran, evaluates the controller, applies the
+    // first-tick rule of the new action (traffic_env.py:225-232); road lanes re-derive their closed-form light limit
+    // with the env's tick count so far (tb) as the origin.
+    s.meta[my_sr] = (uint32_t)ld | ((uint32_t)lc << 8);
+    __syncthreads();
+    if (tid < nI) {
+      const int i = tid, g = i / p.I, ii = i - g * p.I;
+      if (!(GROUPED && envm[ENVM_WORDS * g + ENVM_SKIP])) {
+        const int rel = envm[ENVM_WORDS * g + ENVM_TB] - 1 - envm[ENVM_WORDS * g + ENVM_SEG];   // last tick run, from the segment origin
+        const bool ls_prev = learn_switch && s.act[i];
+        int ph = s.phase[i] ^ (ls_prev ? (rel & 1) : 0);
+        int el = ls_prev ? 0 : s.elapsed[i] + rel;
+        int bal = 0;
+        for (int dd = 0; dd < 4; dd++) {
+          const uint32_t m = s.meta[g * p.R + dd * p.V + ii];
+          const int cn = ring_count(m & 0xff, (m >> 8) & 0xff);
+          bal += dd < 2 ? cn : -cn;
+        }
+        const int act = bal < 0;
+        if (p.actions_out) p.actions_out[(size_t)(step / p.decide_every) * p.num_envs * p.I + ibase + i] = (uint8_t)act;
+        int change;
+        if (learn_switch) { change = act; ph ^= act; } else { change = ph ^ act; ph = act; }
+        el = (el + 1) * (change ? 0 : 1);
+        s.phase[i] = (uint8_t)ph; s.act[i] = (uint8_t)act; s.elapsed[i] = el;
+      }
+    }
+    __syncthreads();
+    if (tid < ng) envm[ENVM_WORDS * tid + ENVM_SEG] = envm[ENVM_WORDS * tid + ENVM_TB];
+    if (is_train) {
+      const bool ls_act = learn_switch && s.act[dst];
+      const int road_phase = (my_road / p.V) < 2;
+      ylim = (ls_act || road_phase == (int)s.phase[dst]) ? 0x7fffffff : tb + YELLOW_TICKS - s.elapsed[dst];
+    }
+  }
   bool frozen = out_of_play;
   for (int t = 0; t < p.K; t++) {
     const int tt = tb + t;     // tick of the launch for my env: arrival-process tick, light clock, birth stamp
@@ -788,7 +828,8 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     if (GROUPED && envm[ENVM_WORDS * g + ENVM_SKIP]) continue;
     const int env = env_first + g;
     const int ov = envm[ENVM_WORDS * g + ENVM_OVF];
-    const int last = envm[ENVM_WORDS * g + ENVM_TB] + ((ov != NO_OVERFLOW) ? ov : p.K - 1);   // the last tick of the launch env g ran
+    // the last tick of the launch env g ran, counted from the tick its current controller decision was applied at
+    const int last = envm[ENVM_WORDS * g + ENVM_TB] + ((ov != NO_OVERFLOW) ? ov : p.K - 1) - envm[ENVM_WORDS * g + ENVM_SEG];
     unsigned char *wire_rec = use_wire ? p.wire + (step_env0 + env) * p.wire_stride : nullptr;
     const bool ls_act = learn_switch && s.act[i];
     const int ph_f = s.phase[i] ^ (ls_act ? (last & 1) : 0);

@@ -224,15 +224,30 @@ class VecTrafficEnv(object):
                                      self._reward.ctypes.data, self._done.ctypes.data, TE_HOST, None))
         return self._obs, self._reward, self._done
 
-    def step_multi(self, n_steps, actions=None, controller="greedy", k=None, lazy=False):
-        """n_steps actor steps in one launch under one controller decision (te_step_multi), host buffers: returns
+    def _controller_spacing(self, spacing, n_steps, controller):
+        """te_set_controller_spacing when it changed; the action buffer te_step_multi reads / writes."""
+        spacing = 0 if (spacing is None or controller != "greedy") else int(spacing)
+        if spacing != getattr(self, "_spacing", 0):
+            check(self._L.te_set_controller_spacing(self._h, spacing))
+            self._spacing = spacing
+        if spacing == 0:
+            return self._act
+        ndec = (n_steps + spacing - 1) // spacing
+        if getattr(self, "_act_multi_n", 0) < ndec:
+            self._act_multi = self._host_array((ndec, self.num_envs, self.intersections), np.uint8)
+            self._act_multi_n = ndec
+        return self._act_multi[:ndec]
+
+    def step_multi(self, n_steps, actions=None, controller="greedy", k=None, lazy=False, spacing=None):
+        """n_steps actor steps in one launch (te_step_multi), host buffers: returns
         (actions uint8[E, I], obs float[n_steps, E, 2r+I], reward float[n_steps, E, I], done uint8[n_steps, E]).
-        controller "greedy": the kernel evaluates algorithms/greedy.py:14-16 at launch; "given": `actions` holds.
-        lazy=True: (actions, WireResult) - see step()."""
+        controller "greedy": the kernel evaluates algorithms/greedy.py:14-16 at launch - and again every `spacing` actor
+        steps when spacing is given (greedy.py's --spacing; actions is then uint8[ceil(n_steps / spacing), E, I]);
+        "given": `actions` holds for the whole launch.  lazy=True: (actions, WireResult) - see step()."""
         k = self.ticks_per_step if k is None else int(k)
         n_steps = int(n_steps)
         if lazy:
-            act, _ = self.step_multi_wire(n_steps, actions, controller, k)
+            act, _ = self.step_multi_wire(n_steps, actions, controller, k, spacing)
             return act, WireResult(self, self._multi_wire[:n_steps])
         if getattr(self, "_multi_n", 0) < n_steps:
             E, I = self.num_envs, self.intersections
@@ -240,14 +255,15 @@ class VecTrafficEnv(object):
                            self._host_array((n_steps, E, I), np.float32), self._host_array((n_steps, E), np.uint8))
             self._multi_n = n_steps
         obs, rew, done = (x[:n_steps] for x in self._multi)
+        act = self._controller_spacing(spacing, n_steps, controller)
         if controller == "greedy":
             ctrl = TE_CTRL_GREEDY
         else:
             ctrl = TE_CTRL_GIVEN
             self._actions(actions)
-        check(self._L.te_step_multi(self._h, n_steps, ctrl, self._act.ctypes.data, k, obs.ctypes.data, rew.ctypes.data,
+        check(self._L.te_step_multi(self._h, n_steps, ctrl, act.ctypes.data, k, obs.ctypes.data, rew.ctypes.data,
                                     done.ctypes.data, TE_HOST, None))
-        return self._act, obs, rew, done
+        return act, obs, rew, done
 
     def _wire_views(self, w):
         """dict of views into a record buffer [..., E, stride]."""
@@ -256,7 +272,7 @@ class VecTrafficEnv(object):
                 "light": w[..., wl.light:wl.light + 4 * I].view(np.float32),
                 "reward": w[..., wl.reward:wl.reward + 4 * I].view(np.float32), "done": w[..., wl.done]}
 
-    def step_multi_wire(self, n_steps, actions=None, controller="greedy", k=None):
+    def step_multi_wire(self, n_steps, actions=None, controller="greedy", k=None, spacing=None):
         """step_multi with the results left as wire records: (actions, dict of views [n_steps, E, ...])."""
         k = self.ticks_per_step if k is None else int(k)
         n_steps = int(n_steps)
@@ -264,16 +280,19 @@ class VecTrafficEnv(object):
             self._multi_wire = self._host_array((n_steps, self.num_envs, self.wire.stride), np.uint8)
             self._multi_wire_n = n_steps
         buf = self._multi_wire[:n_steps]
+        act = self._controller_spacing(spacing, n_steps, controller)
         if controller != "greedy":
             self._actions(actions)
         check(self._L.te_step_multi_wire(self._h, n_steps, TE_CTRL_GREEDY if controller == "greedy" else TE_CTRL_GIVEN,
-                                         self._act.ctypes.data, k, buf.ctypes.data, TE_HOST, None))
-        return self._act, self._wire_views(buf)
+                                         act.ctypes.data, k, buf.ctypes.data, TE_HOST, None))
+        return act, self._wire_views(buf)
 
-    def step_multi_device(self, n_steps, actions, obs, reward, done, controller="greedy", k=None, stream=None):
-        """te_step_multi on caller-owned device buffers ([n_steps, E, ...] outputs; `actions` [E, I] is written by the
-        greedy controller or read when controller == "given"); asynchronous."""
+    def step_multi_device(self, n_steps, actions, obs, reward, done, controller="greedy", k=None, stream=None, spacing=None):
+        """te_step_multi on caller-owned device buffers ([n_steps, E, ...] outputs; `actions` [E, I] - with spacing:
+        [ceil(n_steps / spacing), E, I] - is written by the greedy controller or read when controller == "given");
+        asynchronous."""
         k = self.ticks_per_step if k is None else int(k)
+        self._controller_spacing(spacing, int(n_steps), controller)
         check(self._L.te_step_multi(self._h, int(n_steps), TE_CTRL_GREEDY if controller == "greedy" else TE_CTRL_GIVEN,
                                     _ptr(actions), k, _ptr(obs), _ptr(reward), _ptr(done), TE_DEVICE, stream))
 
