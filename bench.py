@@ -5,8 +5,9 @@ roads (L = 500 m), 16384 env instances per GPU, greedy light controller recomput
 actor steps (algorithms/greedy.py:13-16 with --spacing 3), Philox arrivals at the reference's
 stock --local_cars_per_sec 0.12, Remi(Repeater(10)) semantics, envs pre-rolled to the
 ring-capacity-bound steady state (see DESIGN.md "headline workload").  A step = one actor step
-(10 physics ticks unless a ring overflows) of every env; the 3 actor steps a greedy decision holds for are ONE
-te_step_multi launch with the controller evaluated in the kernel (--no-multi: one te_step launch per step).
+(10 physics ticks unless a ring overflows) of every env; the controller runs inside the kernel, and one te_step_multi
+launch holds as many decisions as fit its 64 ticks: 6 actor steps = 2 greedy decisions (--launch-steps 3: one decision
+per launch; --no-multi: one te_step launch per step + a controller kernel every third).
 
 After the timed region a `secondary` block puts the other BASELINE configs on the same record (every rank takes
 part, values are whole-job aggregates): the default 3x3 grid at 131072 envs per GPU (config 4: 2^20 envs at
@@ -40,6 +41,7 @@ WORKLOADS = {
 }
 K_TICKS = 10      # FLAGS.light_iterations = light_secs / rate = 5 / 0.5 (traffic_test.py:21)
 SPACING = 3       # FLAGS.spacing (alg_flags.py:22)
+MAX_LAUNCH_TICKS = 64   # te_step_multi: n_steps * k_ticks <= 64
 EPISODE_LEN = 120  # FLAGS.episode_len = episode_secs / light_secs = 600 / 5 (traffic_test.py:12-20)
 OPS_PER_UPDATE = 34  # arithmetic ops of one sim() element
 
@@ -56,6 +58,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--launch-steps", type=int, default=0, help="actor steps per te_step_multi launch (a multiple of the "
+                    "controller spacing; default: as many decisions as fit the 64 ticks of a launch = 6; 3 = one decision per launch)")
     ap.add_argument("--no-multi", action="store_true", help="one launch per actor step + a separate greedy-controller "
                     "kernel every `spacing` steps (round-1 scheme) instead of te_step_multi")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -217,7 +221,8 @@ def bench_config(a, w, envs):
             "envs_per_gpu": envs, "policy": "greedy(spacing=%d)" % SPACING, "ticks_per_actor_step": K_TICKS,
             "arrivals": "philox, local_cars_per_sec=%.2f (reference default)" % w["lcps"],
             "wrappers": "Remi(Repeater(10))",
-            "launches": "te_step_multi: the %d actor steps a greedy decision holds for are one launch, controller in the kernel" % SPACING,
+            "launches": "te_step_multi with the controller in the kernel: a new greedy decision every %d actor steps, as many "
+                        "decisions per launch as fit its %d ticks (--launch-steps; default 6 actor steps = 2 decisions)" % (SPACING, MAX_LAUNCH_TICKS),
             "reset": "none (env keeps stepping after overflow, as the bare reference env does); pre-rolled into the "
                      "ring-capacity-bound steady state: ~48 % mean ring occupancy, NOT near-full in the mean (DESIGN.md 7); "
                      "the auto-reset variant is secondary.headline_auto_reset",
@@ -303,20 +308,26 @@ def allreduce(c, vals, op="sum"):
 class Runner(object):
     """One batched env on this rank plus its device-resident and host-side step loops."""
 
-    def __init__(self, c, w, E, policy="greedy", auto_reset=False, episode_len=0, multi=True):
+    def __init__(self, c, w, E, policy="greedy", auto_reset=False, episode_len=0, multi=True, launch_steps=0):
         from traffic_env_b200 import VecTrafficEnv
         torch = c.torch
         self.c, self.w, self.E, self.policy = c, w, E, policy
         # greedy decisions hold for `spacing` actor steps (greedy.py:14-16): those steps are ONE te_step_multi launch with
         # the controller evaluated in the kernel (not for TE_AUTO_RESET handles, which reset between te_step calls)
         self.multi = bool(multi) and policy == "greedy" and not auto_reset
+        # ... and a launch holds as many decisions as fit its 64 ticks (te_set_controller_spacing: the controller is
+        # re-evaluated inside the kernel every `spacing` steps): 6 actor steps = 2 decisions at 10 ticks per step
+        fit = max(SPACING, MAX_LAUNCH_TICKS // K_TICKS // SPACING * SPACING)
+        self.spl = (min(fit, max(SPACING, launch_steps // SPACING * SPACING)) if launch_steps else fit) if self.multi else 1
         self.env = VecTrafficEnv(m=w["m"], n=w["n"], length=w["length"], num_envs=E, local_cars_per_sec=w["lcps"],
                                  arrivals="philox", seed=2026, env_id_base=c.rank * E, device=c.local,
                                  ticks_per_step=K_TICKS, remi=True, auto_reset=auto_reset, episode_len=episode_len)
         env = self.env
         self.I, self.OL = env.intersections, env.obs_len
-        self.d_act = torch.zeros((E, self.I), dtype=torch.uint8, device=c.dev)
-        ns = SPACING if self.multi else 1
+        ns = self.spl
+        self.ndec = (ns + SPACING - 1) // SPACING
+        self.d_acts = torch.zeros((self.ndec, E, self.I), dtype=torch.uint8, device=c.dev)   # one block per decision of a launch
+        self.d_act = self.d_acts[0]                                                           # the action in force
         self.d_obs = torch.empty((ns, E, self.OL), dtype=torch.float32, device=c.dev)
         self.d_rew = torch.empty((ns, E, self.I), dtype=torch.float32, device=c.dev)
         self.d_done = torch.empty((ns, E), dtype=torch.uint8, device=c.dev)
@@ -337,9 +348,14 @@ class Runner(object):
             return
         s = s0
         while s < s0 + n:
-            k = min(SPACING - s % SPACING, s0 + n - s)    # up to the next controller decision
-            self.env.step_multi_device(k, self.d_act, self.d_obs, self.d_rew, self.d_done, controller="greedy" if s % SPACING == 0 else "given",
-                                       stream=self.c.stream)
+            if s % SPACING == 0:      # a launch starts at a controller decision and holds up to spl steps (spl / SPACING decisions)
+                k = min(self.spl, s0 + n - s)
+                self.env.step_multi_device(k, self.d_acts, self.d_obs, self.d_rew, self.d_done, controller="greedy",
+                                           spacing=SPACING, stream=self.c.stream)
+                self.d_act = self.d_acts[(k - 1) // SPACING]
+            else:                     # (a caller that stopped between two decisions: finish the current one)
+                k = min(SPACING - s % SPACING, s0 + n - s)
+                self.env.step_multi_device(k, self.d_act, self.d_obs, self.d_rew, self.d_done, controller="given", stream=self.c.stream)
             self.launches += 1
             s += k
 
@@ -351,10 +367,13 @@ class Runner(object):
             return acc
         s, acc = s0, 0.0
         while s < s0 + n:
-            k = min(SPACING - s % SPACING, s0 + n - s)
-            act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given")
             if s % SPACING == 0:
-                self.h_act[:] = act
+                k = min(self.spl, s0 + n - s)
+                act, obs, rew, done = self.env.step_multi(k, controller="greedy", spacing=SPACING)
+                self.h_act[:] = act[-1]
+            else:
+                k = min(SPACING - s % SPACING, s0 + n - s)
+                act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="given")
             for j in range(k):
                 acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])   # every actor step's result is read on the host
             s += k
@@ -367,10 +386,13 @@ class Runner(object):
         s, acc = s0, 0.0
         while s < s0 + n:
             if self.policy == "greedy" and self.multi:
-                k = min(SPACING - s % SPACING, s0 + n - s)
-                act, res = self.env.step_multi(k, actions=self.h_act, controller="greedy" if s % SPACING == 0 else "given", lazy=True)
                 if s % SPACING == 0:
-                    self.h_act[:] = act
+                    k = min(self.spl, s0 + n - s)
+                    act, res = self.env.step_multi(k, controller="greedy", spacing=SPACING, lazy=True)
+                    self.h_act[:] = act[-1]
+                else:
+                    k = min(SPACING - s % SPACING, s0 + n - s)
+                    act, res = self.env.step_multi(k, actions=self.h_act, controller="given", lazy=True)
                 for j in range(k):
                     acc += float(res.reward[j, 0, 0]) + float(res.obs_of([0], step=j)[0, 0])
             else:
@@ -438,7 +460,7 @@ class Runner(object):
     def timed_host(self, steps, warmup, wire=False):
         c, env = self.c, self.env
         run = self.host_steps_wire if wire else self.host_steps
-        run(warmup)
+        run(max(warmup, self.spl))     # at least one full-size launch: the page-locked result buffers grow on first use
         barrier(c)
         b0 = env.stats()["vehicle_updates"]
         t0 = time.perf_counter()
@@ -451,13 +473,13 @@ class Runner(object):
         return {"value": vu / t, "unit": "vehicle-updates/s", "h2d_bytes_per_step": int(E * I),
                 "d2h_bytes_per_step": int((env.d2h_bytes_per_step() if wire or not env.host_float_dma() else E * (OL * 4 + I * 4 + 1))
                                           + (E * I // SPACING if self.policy == "greedy" else 0)),
-                "steps": steps, "host_calls_per_step": (1.0 / SPACING) if self.multi else (1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0))}
+                "steps": steps, "host_calls_per_step": (1.0 / self.spl) if self.multi else (1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0))}
 
     def kernel_times(self, n):
         """Mean duration of one step-kernel launch (CUDA events on the launch stream, te_last_kernel_ms) and the
         vehicle-updates it processed; a launch is `steps_per_launch` actor steps."""
         kms, kvu = [], []
-        spl = SPACING if self.multi else 1
+        spl = self.spl
         with self.c.torch.cuda.stream(self.c.tstream):
             for i in range(n):
                 b0 = self.env.stats()["vehicle_updates"]
@@ -479,7 +501,7 @@ class Runner(object):
 
     def close(self):
         self.env.close()
-        for k in ("d_act", "d_obs", "d_rew", "d_done", "d_rand"):
+        for k in ("d_act", "d_acts", "d_obs", "d_rew", "d_done", "d_rand"):
             if hasattr(self, k):
                 delattr(self, k)
         self.c.torch.cuda.empty_cache()
@@ -586,7 +608,7 @@ def secondary_block(c, a, arith_peak):
                           "what": "4 envs of each rank's 131072-env default-grid batch vs the CPU oracle (same Philox key): "
                                   "actions, obs, reward, done every step and the final car state, bit for bit; min over ranks"}
     # (i) default grid, 131072 envs per GPU: greedy / no reset (kernel-quality number, comparable across rounds) ...
-    r3 = Runner(c, w3, E3, policy="greedy", multi=not a.no_multi)
+    r3 = Runner(c, w3, E3, policy="greedy", multi=not a.no_multi, launch_steps=a.launch_steps)
     with c.torch.cuda.stream(c.tstream):
         r3.device_steps(w3["preroll"])
     d = r3.timed_device(steps, warm)
@@ -664,7 +686,7 @@ def b200_arm(a):
     w = WORKLOADS[a.workload]
     E = a.envs or w["envs"]
     preroll = w["preroll"] if a.preroll < 0 else a.preroll
-    run = Runner(c, w, E, policy="greedy", multi=not a.no_multi)
+    run = Runner(c, w, E, policy="greedy", multi=not a.no_multi, launch_steps=a.launch_steps)
     env = run.env
     I, OL = run.I, run.OL
     sampler = ClockSampler(c.local)
@@ -683,7 +705,7 @@ def b200_arm(a):
 
     # per-launch kernel time (CUDA events on the launch stream, separate pass so the sync does not sit in the timed region)
     k_ms, k_vu = run.kernel_times(min(a.steps, 10))
-    spl = SPACING if run.multi else 1                      # actor steps per launch
+    spl = run.spl                                          # actor steps per launch
     cars_env = k_vu / E / spl / (loc["ticks"] / max(loc["actor_steps"], 1))
     R, r = env.roads, env.train_roads
     arr_per_step = loc["cars_generated"] / max(loc["actor_steps"], 1)
@@ -705,11 +727,11 @@ def b200_arm(a):
         e2e_float = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)))
         e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
         e2e["api"] = ("VecTrafficEnv.step_multi(n, controller='greedy', lazy=True) -> te_step_multi_wire(TE_HOST): one call per "
-                      "greedy decision (%d actor steps); actions host -> device (given) or back (chosen by the kernel); per actor "
+                      "launch (%d actor steps, a greedy decision every %d); actions host -> device (given) or back (chosen by the kernel); per actor "
                       "step the results of EVERY env arrive in page-locked host memory as compact wire records (%d B per env: u8 "
                       "passed / detected, f32 light / reward, u8 done - lossless: the counts are small integers); the float "
                       "observation is expanded on demand (WireResult.obs / obs_of), here for one env per step, and read" %
-                      (SPACING, env.wire.stride))
+                      (run.spl, SPACING, env.wire.stride))
         e2e_float["api"] = ("the eager form of the same call (lazy=False): every env's float obs[%d] / reward / done in host "
                             "memory every actor step - %s" % (env.obs_len, "float arrays written by the copy engine (few host "
                             "cores per GPU)" if env.host_float_dma() else "wire records expanded by %s helper threads of the handle "
