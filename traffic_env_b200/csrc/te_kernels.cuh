@@ -106,7 +106,8 @@ struct StepParams {
   //   u8 passed[r] | u8 detected[r] | f32 light[I] | f32 reward[I] | u8 done | pad   (wire_stride bytes, see wire_layout)
   unsigned char *wire;
   int wire_stride;
-  // multi-step launches (te_step_multi): nsteps actor steps of K ticks each under one controller decision; the outputs
+  // multi-step launches (te_step_multi): nsteps actor steps of K ticks each (one controller decision, or one every
+  // decide_every steps); the outputs
   // of actor step j go to obs / reward / done / wire + j * (their size for num_envs envs)
   int nsteps;
   int controller;               // CTRL_GIVEN: `actions` is read; CTRL_GREEDY: computed in the kernel from the ring counts
@@ -140,7 +141,7 @@ __host__ __device__ inline uint32_t pack_meta(int leading, int lastcar, int dete
 // ("super-roads": row g * R + road), per-intersection arrays are indexed g * I + intersection.  Every offset is a
 // compile-time function of the kernel variant's row capacity MAXT (>= G * R rounded up to whole warps) so that the tick
 // loop addresses shared memory with immediates; only the tail has a run-time size: per env the arrival-count table
-// (K * n_entry bytes), the Philox (draw, skip) snapshots before each tick and two per-env tick stamps.
+// (K * n_entry bytes) and the Philox (draw, skip) snapshots before each tick.
 enum : int { ENVM_OVF = 0,    // first overflowing tick of the current actor step (NO_OVERFLOW: none yet)
              ENVM_ORD = 1,    // last tick of the launch (CTA-wide count) that needs ordered transfers
              ENVM_TB = 2,     // ticks this env ran in the earlier actor steps of this launch
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(MAXT, MINB) te_step_kernel(const StepParams p)
     for (int g = 0; g < ng; g++) nactive += p.env_mask[env_first + g] != 0;
     if (nactive == 0) return;
   }
-  // run-time tail of the shared-memory layout (per env: arrival counts, Philox snapshots, ENVM words)
+  // run-time tail of the shared-memory layout (per env: arrival counts, Philox snapshots)
   const int cnt_stride = cnt_stride_bytes(KT, p.n_entry);
   uint32_t *const snap_base = reinterpret_cast<uint32_t *>(s.cnt + tail_snap_offset(KT, p.n_entry, G));
   int *const envm = s.envm;
