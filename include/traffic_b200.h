@@ -225,6 +225,9 @@ int te_set_state(te_handle *h, int32_t env_begin, int32_t count, const int32_t *
    fallback are not compiled into the kernels that run.  One wild car in te_set_state switches the
    handle to the checked kernels for good.  v_cap may be NULL. */
 int te_is_tame(const te_handle *h, int32_t *tame, float *v_cap);
+/* The speed cap of the tame domain for an archetype / tick length / road length, 0 when the archetype is outside the
+   supported ranges (host arithmetic only: needs no device). */
+int te_tame_speed_cap(const float *archetype, float rate, float length, float *v_cap);
 
 /* Counters since te_create (device -> host; synchronises the device). */
 int te_get_stats(te_handle *h, te_stats *out);

@@ -1060,6 +1060,14 @@ extern "C" int te_set_state(te_handle *h, int32_t env_begin, int32_t count, cons
   return 0;
 }
 
+extern "C" int te_tame_speed_cap(const float *archetype, float rate, float length, float *v_cap) {
+  if (!archetype || !v_cap) return fail("te_tame_speed_cap: null argument");
+  te_config cfg; te_default_config(&cfg);
+  memcpy(cfg.archetype, archetype, sizeof(cfg.archetype)); cfg.rate = rate; cfg.length = length;
+  tame_archetype(&cfg, v_cap);
+  return 0;
+}
+
 extern "C" int te_is_tame(const te_handle *h, int32_t *tame, float *v_cap) {
   if (!h || !tame) return fail("te_is_tame: null argument");
   *tame = h->tame ? 1 : 0;
