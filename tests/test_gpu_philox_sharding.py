@@ -221,12 +221,15 @@ def test_host_path_slices_equal_single_launch():
 
 @pytest.mark.parametrize("m,n,L,E,S,lcps,multi", [(3, 3, 250.0, 48, 1200, 0.12, False), (10, 10, 500.0, 4, 330, 0.12, False),
                                                    (5, 4, 150.0, 16, 400, 0.2, False), (3, 3, 250.0, 49, 900, 0.12, True),
-                                                   (10, 10, 500.0, 3, 330, 0.12, True)])
+                                                   (10, 10, 500.0, 3, 330, 0.12, True), (3, 3, 250.0, 50, 900, 0.12, 6),
+                                                   (10, 10, 500.0, 3, 330, 0.12, 6), (4, 4, 120.0, 21, 360, 0.3, 6)])
 def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps, multi):
     """Long runs (up to 12000 ticks per env, no reset: the env keeps stepping after overflows, greedy lights every
     third step as in the bench) against the oracle on the same Philox stream: every actor step's observation,
     reward and done flag, and the final ring state, bit for bit.  Reaches the states a short run does not: dense
-    steady state, wrapped rings everywhere, the rare full-powf and generic-arithmetic lanes."""
+    steady state, wrapped rings everywhere, the rare full-powf and generic-arithmetic lanes.  multi = True: one launch per
+    greedy decision (3 actor steps); multi = 6: two decisions per launch (te_set_controller_spacing) - the second one is
+    taken inside the kernel and checked here against the oracle's ring counts at that moment."""
     from traffic_env_b200 import VecTrafficEnv
     from traffic_env_b200.arrivals import gap_cdf
     from tests.golden_util import live_walk
@@ -245,7 +248,13 @@ def test_long_horizon_soak_vs_oracle(m, n, L, E, S, lcps, multi):
     act = np.zeros((E, I), np.uint8)
     for s in range(S):
         if s % 3 == 0:
-            if multi:   # the bench's scheme: the three actor steps of a greedy decision are one launch, controller in the kernel
+            if multi == 6:   # the bench's scheme: six actor steps = two greedy decisions per launch, controller in the kernel
+                if s % 6 == 0:
+                    acts6, obs6, rew6, done6 = env.step_multi(6, controller="greedy", spacing=3)
+                    acts6 = acts6.copy()
+                half = (s % 6) // 3
+                act, obs3, rew3, done3 = acts6[half], obs6[3 * half:], rew6[3 * half:], done6[3 * half:]
+            elif multi:   # the three actor steps of a greedy decision are one launch
                 act, obs3, rew3, done3 = env.step_multi(3, controller="greedy")
                 act = act.copy()
             else:
