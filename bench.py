@@ -332,7 +332,8 @@ class Runner(object):
         self.d_rew = torch.empty((ns, E, self.I), dtype=torch.float32, device=c.dev)
         self.d_done = torch.empty((ns, E), dtype=torch.uint8, device=c.dev)
         self.launches = 0
-        self.h_act = np.zeros((E, self.I), dtype=np.uint8)
+        self.h_act = env.host_buffer((E, self.I), np.uint8)     # page-locked: the agent's actions cross PCIe from here
+        self.h_act[:] = 0
         if policy == "random":
             g = torch.Generator(device=c.dev).manual_seed(1234 + c.rank)
             self.d_rand = torch.randint(0, 2, (8, E, self.I), dtype=torch.uint8, device=c.dev, generator=g)
@@ -376,6 +377,27 @@ class Runner(object):
                 act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="given")
             for j in range(k):
                 acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])   # every actor step's result is read on the host
+            s += k
+        return acc
+
+    def host_steps_agent(self, n, s0=0, lazy=True):
+        """The greedy AGENT on the host, as algorithms/greedy.py:13-17 runs it: every `spacing` actor steps it asks the env
+        for its decision (the ring counts stay on the device: te_greedy_actions evaluates greedy.py:14-16 there and copies
+        the actions device -> host), then steps with THAT action: actions host -> device from page-locked memory, one
+        te_step_multi launch for the steps the decision holds for, every actor step's results device -> host."""
+        s, acc = s0, 0.0
+        while s < s0 + n:
+            if s % SPACING == 0:
+                self.env.greedy_actions(out=self.h_act)
+            k = min(SPACING - s % SPACING, s0 + n - s)
+            if lazy:
+                act, res = self.env.step_multi(k, actions=self.h_act, controller="given", lazy=True)
+                for j in range(k):
+                    acc += float(res.reward[j, 0, 0]) + float(res.obs_of([0], step=j)[0, 0])
+            else:
+                act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="given")
+                for j in range(k):
+                    acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])
             s += k
         return acc
 
@@ -457,9 +479,14 @@ class Runner(object):
         return dict(ms=ms_max, local=d, vu=tot[0], ticks=tot[1], asteps=tot[2], gen=tot[3], ovf=tot[4], episodes=tot[5],
                     launches=self.launches)
 
-    def timed_host(self, steps, warmup, wire=False):
+    def timed_host(self, steps, warmup, wire=False, agent=False):
+        """agent=True: actions come from the host every decision (host_steps_agent); else the controller runs in the kernel."""
         c, env = self.c, self.env
-        run = self.host_steps_wire if wire else self.host_steps
+        agent = agent and self.policy == "greedy" and self.multi
+        if agent:
+            run = lambda n: self.host_steps_agent(n, lazy=wire)     # noqa: E731
+        else:
+            run = self.host_steps_wire if wire else self.host_steps
         run(max(warmup, self.spl))     # at least one full-size launch: the page-locked result buffers grow on first use
         barrier(c)
         b0 = env.stats()["vehicle_updates"]
@@ -470,10 +497,16 @@ class Runner(object):
         vu = allreduce(c, [env.stats()["vehicle_updates"] - b0])[0]
         t = allreduce(c, [dt], "max")[0]
         E, I, OL = self.E, self.I, self.OL
-        return {"value": vu / t, "unit": "vehicle-updates/s", "h2d_bytes_per_step": int(E * I),
+        if agent:
+            h2d, calls = E * I // SPACING, 2.0 / SPACING            # actions up once per decision; greedy_actions + step_multi
+        elif self.multi:
+            h2d, calls = 0, 1.0 / self.spl                           # controller in the kernel: nothing goes up
+        else:
+            h2d, calls = E * I, 1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0)
+        return {"value": vu / t, "unit": "vehicle-updates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int((env.d2h_bytes_per_step() if wire or not env.host_float_dma() else E * (OL * 4 + I * 4 + 1))
                                           + (E * I // SPACING if self.policy == "greedy" else 0)),
-                "steps": steps, "host_calls_per_step": (1.0 / self.spl) if self.multi else (1.0 + (1.0 / SPACING if self.policy == "greedy" else 0.0))}
+                "steps": steps, "host_calls_per_step": calls}
 
     def kernel_times(self, n):
         """Mean duration of one step-kernel launch (CUDA events on the launch stream, te_last_kernel_ms) and the
@@ -613,12 +646,14 @@ def secondary_block(c, a, arith_peak):
         r3.device_steps(w3["preroll"])
     d = r3.timed_device(steps, warm)
     k_ms, k_vu = r3.kernel_times(min(steps, 8))
-    e2e_float = r3.timed_host(max(3, steps // 2), 3)
-    e2e = r3.timed_host(max(3, steps // 2), 3, wire=True)
+    e2e_float = r3.timed_host(max(3, steps // 2), 3, agent=True)
+    e2e = r3.timed_host(max(3, steps // 2), 3, wire=True, agent=True)
+    e2e_dc = r3.timed_host(max(3, steps // 2), 3, wire=True)
     occ = r3.occupancy()
     out["grid3x3_L250_greedy"] = {
         "value": d["vu"] / (d["ms"] * 1e-3), "unit": "vehicle-updates/s", "envs_per_gpu": E3, "envs_total": E3 * c.world,
-        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_float": e2e_float, "kernel_ms": k_ms,
+        "ms_per_step": d["ms"] / steps, "steps": steps, "e2e": e2e, "e2e_float": e2e_float, "e2e_device_controller": e2e_dc,
+        "kernel_ms": k_ms,
         "env_actor_steps_per_sec": d["asteps"] / (d["ms"] * 1e-3),
         "roofline_compute": {"achieved": k_vu / (k_ms * 1e-3), "peak": arith_peak,
                              "frac": (k_vu / (k_ms * 1e-3) / arith_peak) if arith_peak else None},
@@ -722,17 +757,25 @@ def b200_arm(a):
     traffic, traffic_note = measured_traffic(a.workload)
 
     # end to end through the public API with HOST buffers: what the greedy agent does (greedy.py:13-17)
-    e2e = e2e_float = None
+    # `e2e` / `e2e_float`: the AGENT is on the host - its actions go host -> device every decision, every actor step's results
+    # come device -> host; `e2e_device_controller`: the same with the controller inside the kernel (nothing goes up).
+    e2e = e2e_float = e2e_dc = None
     if not a.no_e2e:
-        e2e_float = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)))
-        e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
-        e2e["api"] = ("VecTrafficEnv.step_multi(n, controller='greedy', lazy=True) -> te_step_multi_wire(TE_HOST): one call per "
-                      "launch (%d actor steps, a greedy decision every %d); actions host -> device (given) or back (chosen by the kernel); per actor "
+        e2e_float = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), agent=True)
+        e2e = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True, agent=True)
+        e2e_dc = run.timed_host(max(10, a.steps), max(3, min(a.warmup, 5)), wire=True)
+        e2e["api"] = ("the greedy agent on the host (greedy.py:13-17): every %d actor steps VecTrafficEnv.greedy_actions(out=pinned) "
+                      "(greedy.py:14-16 evaluated on the device-resident ring counts, actions device -> host), then "
+                      "VecTrafficEnv.step_multi(%d, actions=pinned, controller='given', lazy=True) -> te_step_multi_wire(TE_HOST): "
+                      "actions host -> device from page-locked memory, one launch for the steps the decision holds for; per actor "
                       "step the results of EVERY env arrive in page-locked host memory as compact wire records (%d B per env: u8 "
                       "passed / detected, f32 light / reward, u8 done - lossless: the counts are small integers); the float "
                       "observation is expanded on demand (WireResult.obs / obs_of), here for one env per step, and read" %
-                      (run.spl, SPACING, env.wire.stride))
-        e2e_float["api"] = ("the eager form of the same call (lazy=False): every env's float obs[%d] / reward / done in host "
+                      (SPACING, SPACING, env.wire.stride))
+        e2e_dc["api"] = ("VecTrafficEnv.step_multi(%d, controller='greedy', spacing=%d, lazy=True): the controller runs inside the "
+                         "kernel (no host -> device traffic; the chosen actions come back), %d actor steps per launch, results as "
+                         "for e2e" % (run.spl, SPACING, run.spl))
+        e2e_float["api"] = ("the eager form of the e2e call (lazy=False): every env's float obs[%d] / reward / done in host "
                             "memory every actor step - %s" % (env.obs_len, "float arrays written by the copy engine (few host "
                             "cores per GPU)" if env.host_float_dma() else "wire records expanded by %s helper threads of the handle "
                             "while the next slices are simulated" % os.environ.get("TE_HOST_THREADS")))
@@ -774,7 +817,7 @@ def b200_arm(a):
             "ordered_transfer_ticks_frac_rank0": loc["seq_fallback_ticks"] / max(loc["ticks"], 1),
             "steady_state_occupancy_rank0": occ,
             "target_8gpu": 1e11, "frac_of_per_gpu_target": value / c.world / 1.25e10,
-            "clocks": clocks, "e2e": e2e, "e2e_float": e2e_float, "gpu_launches": n_launch,
+            "clocks": clocks, "e2e": e2e, "e2e_float": e2e_float, "e2e_device_controller": e2e_dc, "gpu_launches": n_launch,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_note, "kernel": "te_step_kernel", "kernel_ms": k_ms,
                          "actor_steps_per_launch": spl, "algorithmic_bytes_per_env_launch": bytes_env, "cars_per_env": cars_env,

@@ -371,10 +371,17 @@ class VecTrafficEnv(object):
         c = self.cars_on_roads_flat()[:, :self.train_roads]
         return np.transpose(c.reshape(self.num_envs, 4, self.m, self.n), (0, 2, 3, 1))
 
+    def host_buffer(self, shape, dtype):
+        """A page-locked host array owned by this env (te_host_alloc): for actions and results that cross PCIe every step."""
+        return self._host_array(tuple(shape), dtype)
+
     def greedy_actions(self, out=None, stream=None):
-        """algorithms/greedy.py:14-16 for every env; host array by default, or into a device buffer `out`."""
-        if out is None:
-            out = np.empty((self.num_envs, self.intersections), np.uint8)
+        """algorithms/greedy.py:14-16 for every env; a new host array by default, into the host array `out` (uint8[E, I],
+        C-contiguous; page-locked memory from host_buffer() avoids a staging copy), or into a device buffer `out`."""
+        if out is None or isinstance(out, np.ndarray):
+            if out is None:
+                out = np.empty((self.num_envs, self.intersections), np.uint8)
+            assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.num_envs * self.intersections
             check(self._L.te_greedy_actions(self._h, out.ctypes.data, TE_HOST, None))
             return out
         check(self._L.te_greedy_actions(self._h, _ptr(out), TE_DEVICE, stream))
