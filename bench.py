@@ -305,6 +305,22 @@ def allreduce(c, vals, op="sum"):
     return [float(x) for x in t.tolist()]
 
 
+def launch_plan(s0, n, spl, spacing=SPACING):
+    """The te_step_multi launches that cover actor steps [s0, s0 + n): a list of (steps, controller).  A launch starts at a
+    controller decision (step index divisible by `spacing`) and holds up to `spl` steps - spl / spacing decisions, taken
+    inside the kernel; a range that starts between two decisions first finishes the current one ("given": the action in
+    force).  Decisions therefore fall on the same step indices whatever the launch length."""
+    plan, s = [], s0
+    while s < s0 + n:
+        if s % spacing == 0:
+            k, ctrl = min(spl, s0 + n - s), "greedy"
+        else:
+            k, ctrl = min(spacing - s % spacing, s0 + n - s), "given"
+        plan.append((k, ctrl))
+        s += k
+    return plan
+
+
 class Runner(object):
     """One batched env on this rank plus its device-resident and host-side step loops."""
 
@@ -347,18 +363,14 @@ class Runner(object):
             for s in range(s0, s0 + n):
                 self.device_step(s)
             return
-        s = s0
-        while s < s0 + n:
-            if s % SPACING == 0:      # a launch starts at a controller decision and holds up to spl steps (spl / SPACING decisions)
-                k = min(self.spl, s0 + n - s)
+        for k, ctrl in launch_plan(s0, n, self.spl):
+            if ctrl == "greedy":
                 self.env.step_multi_device(k, self.d_acts, self.d_obs, self.d_rew, self.d_done, controller="greedy",
                                            spacing=SPACING, stream=self.c.stream)
                 self.d_act = self.d_acts[(k - 1) // SPACING]
-            else:                     # (a caller that stopped between two decisions: finish the current one)
-                k = min(SPACING - s % SPACING, s0 + n - s)
+            else:
                 self.env.step_multi_device(k, self.d_act, self.d_obs, self.d_rew, self.d_done, controller="given", stream=self.c.stream)
             self.launches += 1
-            s += k
 
     def host_steps(self, n, s0=0):
         if not self.multi:
@@ -366,18 +378,15 @@ class Runner(object):
             for s in range(s0, s0 + n):
                 acc += self.host_step(s)
             return acc
-        s, acc = s0, 0.0
-        while s < s0 + n:
-            if s % SPACING == 0:
-                k = min(self.spl, s0 + n - s)
+        acc = 0.0
+        for k, ctrl in launch_plan(s0, n, self.spl):
+            if ctrl == "greedy":
                 act, obs, rew, done = self.env.step_multi(k, controller="greedy", spacing=SPACING)
                 self.h_act[:] = act[-1]
             else:
-                k = min(SPACING - s % SPACING, s0 + n - s)
                 act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="given")
             for j in range(k):
                 acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])   # every actor step's result is read on the host
-            s += k
         return acc
 
     def host_steps_agent(self, n, s0=0, lazy=True):
@@ -385,11 +394,10 @@ class Runner(object):
         for its decision (the ring counts stay on the device: te_greedy_actions evaluates greedy.py:14-16 there and copies
         the actions device -> host), then steps with THAT action: actions host -> device from page-locked memory, one
         te_step_multi launch for the steps the decision holds for, every actor step's results device -> host."""
-        s, acc = s0, 0.0
-        while s < s0 + n:
-            if s % SPACING == 0:
+        acc = 0.0
+        for k, ctrl in launch_plan(s0, n, SPACING):     # one launch per decision: the agent decides on the host
+            if ctrl == "greedy":
                 self.env.greedy_actions(out=self.h_act)
-            k = min(SPACING - s % SPACING, s0 + n - s)
             if lazy:
                 act, res = self.env.step_multi(k, actions=self.h_act, controller="given", lazy=True)
                 for j in range(k):
@@ -398,36 +406,32 @@ class Runner(object):
                 act, obs, rew, done = self.env.step_multi(k, actions=self.h_act, controller="given")
                 for j in range(k):
                     acc += float(rew[j, 0, 0]) + float(obs[j, 0, 0])
-            s += k
         return acc
 
     def host_steps_wire(self, n, s0=0):
         """host_steps through the lazy form of the same calls (step(..., lazy=True) / step_multi(..., lazy=True)): every
         env's results arrive in page-locked host memory as compact wire records, the float observation is expanded on
         demand - here for one env per actor step, which is also read."""
-        s, acc = s0, 0.0
-        while s < s0 + n:
-            if self.policy == "greedy" and self.multi:
-                if s % SPACING == 0:
-                    k = min(self.spl, s0 + n - s)
+        acc = 0.0
+        if self.policy == "greedy" and self.multi:
+            for k, ctrl in launch_plan(s0, n, self.spl):
+                if ctrl == "greedy":
                     act, res = self.env.step_multi(k, controller="greedy", spacing=SPACING, lazy=True)
                     self.h_act[:] = act[-1]
                 else:
-                    k = min(SPACING - s % SPACING, s0 + n - s)
                     act, res = self.env.step_multi(k, actions=self.h_act, controller="given", lazy=True)
                 for j in range(k):
                     acc += float(res.reward[j, 0, 0]) + float(res.obs_of([0], step=j)[0, 0])
+            return acc
+        for s in range(s0, s0 + n):         # one te_step per actor step
+            if self.policy == "greedy":
+                if s % SPACING == 0:
+                    self.h_act[:] = self.env.greedy_actions()
+                a = self.h_act
             else:
-                k = 1
-                if self.policy == "greedy":
-                    if s % SPACING == 0:
-                        self.h_act[:] = self.env.greedy_actions()
-                    a = self.h_act
-                else:
-                    a = self.h_rand[s % 8]
-                res = self.env.step(a, lazy=True)
-                acc += float(res.reward[0, 0]) + float(res.obs_of([0])[0, 0])
-            s += k
+                a = self.h_rand[s % 8]
+            res = self.env.step(a, lazy=True)
+            acc += float(res.reward[0, 0]) + float(res.obs_of([0])[0, 0])
         return acc
 
     def device_step(self, s):

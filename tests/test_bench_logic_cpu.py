@@ -50,3 +50,26 @@ def test_traffic_figure_is_refused_when_sources_changed(tmp_path, monkeypatch):
     monkeypatch.setattr(bench, "kernel_source_sha", lambda: "0" * 16)
     val, why = bench.measured_traffic("w")
     assert val is None and "stale" in why
+
+
+def test_launch_plan_keeps_decisions_on_the_same_steps():
+    """bench.launch_plan: whatever the launch length and wherever a range starts, the launches cover exactly the
+    requested steps, "greedy" launches start on a decision step and hold whole decisions (except at the end of the range),
+    and the set of decision steps is the same as with one launch per decision."""
+    sp = bench.SPACING
+    for spl in (sp, 2 * sp, 4 * sp):
+        for s0 in range(0, 8):
+            for n in range(0, 30):
+                plan = bench.launch_plan(s0, n, spl)
+                assert sum(k for k, _ in plan) == n and all(k >= 1 for k, _ in plan)
+                s, decisions = s0, []
+                for k, ctrl in plan:
+                    if ctrl == "greedy":
+                        assert s % sp == 0 and k <= spl
+                        decisions += list(range(s, s + k, sp))
+                    else:
+                        assert s % sp != 0 and k <= sp - s % sp      # finishes the decision in force, never crosses one
+                    s += k
+                assert decisions == [t for t in range(s0, s0 + n) if t % sp == 0]
+    assert bench.launch_plan(0, 21, 6) == [(6, "greedy"), (6, "greedy"), (6, "greedy"), (3, "greedy")]
+    assert bench.launch_plan(4, 10, 6) == [(2, "given"), (6, "greedy"), (2, "greedy")]
